@@ -37,7 +37,7 @@ extern "C" {
 #define USIM_TASK_DIM 48     /* per-env task-state record, layout below */
 #define USIM_MAX_ACTION 7
 #define USIM_NV_ARM 7
-#define USIM_MAX_CONTACTS 224 /* per env (reference: nconmax 5000 for the whole scene) */
+#define USIM_MAX_CONTACTS 160 /* per env (reference: nconmax 5000 for the whole scene) */
 
 /* impedance modes of the OSC_POSE controller (rl_config.yaml:41, main.py:33) */
 enum { USIM_MODE_FIXED = 0, USIM_MODE_TRACKING = 1, USIM_MODE_VARIABLE_Z = 2, USIM_MODE_WRENCH = 3 };

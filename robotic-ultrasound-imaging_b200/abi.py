@@ -15,7 +15,7 @@ from .model import UltrasoundModel
 USIM_ABI_VERSION = 1
 OBS_DIM = 19
 TASK_DIM = 48
-MAX_CONTACTS = 224
+MAX_CONTACTS = 160
 DIAG_DIM = 24
 
 MODE_FIXED, MODE_TRACKING, MODE_VARIABLE_Z, MODE_WRENCH = 0, 1, 2, 3

@@ -1,0 +1,388 @@
+// usim.cu — C ABI (include/usim.h) over the sm_100a kernels.  Owns the per-env state in HBM.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "arm.cuh"
+#include "common.cuh"
+#include "soft.cuh"
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) {
+  g_err = m;
+  return -1;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+struct usim_handle {
+  int device = 0, n = 0, nq = 0, nv = 0, adim = 6, soft = 0;
+  DevModel hm;
+  // per-env state, env-major rows (one warp owns one row -> one coalesced 128-B aligned stream)
+  float *qpos = nullptr, *qvel = nullptr, *warm = nullptr, *task = nullptr, *armbuf = nullptr, *diag = nullptr;
+  int *ncon = nullptr, *geom1 = nullptr, *geom2 = nullptr;
+  float* cdist = nullptr;
+  // model tables
+  float *part_pos = nullptr, *part_axis = nullptr, *iw_dof = nullptr, *iw_body = nullptr;
+  int *nbr = nullptr, *eq_pairs = nullptr;
+  short* nbr_pair = nullptr;
+  // staging for the host-buffer path
+  float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_tobs = nullptr;
+  uint8_t* h_done = nullptr;
+  float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_tobs = nullptr;
+  uint8_t* d_done = nullptr;
+  uint8_t* d_resetmask = nullptr;
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  int64_t launches = 0, timed_launches = 0;
+  double timed_ms = 0.0;
+  size_t smem = 0;
+};
+
+const char* usim_last_error(void) { return g_err.c_str(); }
+int usim_abi_version(void) { return USIM_ABI_VERSION; }
+
+template <typename T>
+static cudaError_t upload(T** dst, const std::vector<T>& v) {
+  cudaError_t e = cudaMalloc((void**)dst, std::max<size_t>(v.size(), 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (!v.empty()) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return e;
+}
+
+int usim_create(const usim_model* m, const usim_config* c, int device, usim_handle** out) {
+  if (!m || !c || !out) return fail("usim_create: null argument");
+  if (c->abi_version != USIM_ABI_VERSION) return fail("usim_create: ABI version mismatch");
+  if (c->num_envs <= 0) return fail("usim_create: num_envs must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("usim_create: no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("usim_create: bad device index");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail("usim_create: kernels are built for sm_100a only; found sm_" + std::to_string(prop.major * 10 + prop.minor));
+  if (m->soft && (m->npart > NPART_MAX || m->npair > NPAIR_MAX)) return fail("usim_create: composite larger than the compiled limits");
+  int substeps = (int)((1.0 / c->control_freq) / m->timestep + 1e-9);
+  if (substeps != 1) return fail("usim_create: control_freq must equal 1/timestep (one physics step per control step; rl_config.yaml:26)");
+
+  usim_handle* h = new usim_handle();
+  h->device = device; h->n = c->num_envs; h->nq = m->nq; h->nv = m->nv; h->soft = m->soft;
+  h->adim = c->impedance_mode == USIM_MODE_VARIABLE_Z ? 7 : 6;
+  DevModel& d = h->hm;
+  memset(&d, 0, sizeof d);
+  for (int j = 0; j < 7; j++) {
+    const double* L = m->arm_link + 22 * j;
+    for (int k = 0; k < 3; k++) { d.link_pos[j][k] = (float)L[k]; d.link_com[j][k] = (float)L[12 + k]; }
+    for (int k = 0; k < 9; k++) d.link_R[j][k] = (float)L[3 + k];
+    d.link_mass[j] = (float)L[15];
+    for (int k = 0; k < 6; k++) d.link_I[j][k] = (float)L[16 + k];
+    d.jnt_lo[j] = (float)m->jnt_range[2 * j]; d.jnt_hi[j] = (float)m->jnt_range[2 * j + 1];
+    d.ctrl[j] = (float)m->ctrl_range[j]; d.init_qpos[j] = (float)m->init_qpos[j];
+    d.iw_arm[j] = (float)m->dof_invweight0[j];
+  }
+  for (int k = 0; k < 34; k++) d.tool[k] = (float)m->arm_tool[k];
+  d.arm_damp = (float)m->dof_damping[0];
+  d.h = (float)m->timestep; d.impratio = (float)m->impratio;
+  for (int k = 0; k < 3; k++) d.g[k] = (float)m->gravity[k];
+  for (int k = 0; k < 2; k++) { d.solref[k] = (float)m->solref[k]; d.solref_smooth[k] = (float)m->solref_smooth[k]; }
+  for (int k = 0; k < 5; k++) d.solimp[k] = (float)m->solimp[k];
+  d.table_z = (float)m->table_top_z; d.table_half = (float)m->table_half_xy;
+  d.fr_table_probe = (float)fmax(m->table_friction, m->probe_friction);
+  d.fr_table_part = (float)fmax(m->table_friction, m->particle_friction);
+  d.fr_probe_part = (float)fmax(m->probe_friction, m->particle_friction);
+  d.probe_r = (float)m->probe_radius; d.cap_r = (float)m->cap_radius;
+  d.iw_probe = (float)m->body_invweight0[2 * m->probe_body]; d.iw_table = 0.f;
+  d.soft = m->soft; d.npart = m->soft ? m->npart : 0; d.npair = m->soft ? m->npair : 0;
+  std::vector<float> ppos, paxis, iwd, iwb;
+  std::vector<int> nbr, pairs;
+  std::vector<short> nbrp;
+  if (m->soft) {
+    int np = m->npart;
+    d.tendon_iw = (float)m->tendon_invweight0;
+    d.free_damp = (float)m->dof_damping[7];
+    d.part_mass = (float)m->body_mass[m->part_body0];
+    d.center_mass = (float)m->body_mass[m->torso_body];
+    for (int k = 0; k < 7; k++) d.torso_qpos0[k] = (float)m->qpos0[7 + k];
+    // capsule half length from the two segment ends of particle 0
+    double dd = 0;
+    for (int k = 0; k < 3; k++) { double t = m->part_seg_outer[k] - m->part_seg_inner[k]; dd += t * t; }
+    d.cap_hl = (float)(0.5 * sqrt(dd));
+    // constant rotational inertia: sum of the body-frame inertias of every torso body about its own COM
+    double rot[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = m->torso_body; b < m->torso_body + 1 + np; b++) {
+      const double* I = m->body_inertia + 9 * b;
+      rot[0] += I[0]; rot[1] += I[4]; rot[2] += I[8]; rot[3] += I[1]; rot[4] += I[2]; rot[5] += I[5];
+    }
+    for (int k = 0; k < 6; k++) d.rot_I[k] = (float)rot[k];
+    for (int i = 0; i < np; i++) {
+      for (int k = 0; k < 3; k++) { ppos.push_back((float)m->part_pos[3 * i + k]); paxis.push_back((float)m->part_axis[3 * i + k]); }
+      iwd.push_back((float)m->dof_invweight0[13 + i]);
+      iwb.push_back((float)m->body_invweight0[2 * (m->part_body0 + i)]);
+      for (int k = 0; k < 6; k++) nbr.push_back(m->part_nbr[6 * i + k]);
+    }
+    nbrp.assign((size_t)np * 6, -1);
+    for (int p = 0; p < m->npair; p++) {
+      int a = m->eq_pairs[2 * p], b = m->eq_pairs[2 * p + 1];
+      pairs.push_back(a); pairs.push_back(b);
+      for (int side = 0; side < 2; side++) {
+        int i = side ? b : a, j = side ? a : b;
+        for (int k = 0; k < 6; k++)
+          if (nbr[6 * i + k] == j) nbrp[6 * i + k] = (short)p;
+      }
+    }
+  }
+  d.mode = c->impedance_mode; d.horizon = c->horizon; d.early_term = c->early_termination;
+  d.solref_rand = c->solref_randomization; d.pos_rand = c->probe_pos_randomization; d.det_traj = c->deterministic_trajectory;
+  d.uncouple = c->uncouple_pos_ori; d.iters = c->solver_iterations > 0 ? c->solver_iterations : 40;
+  d.adim = h->adim; d.env_off = c->env_id_offset; d.nq = m->nq; d.nv = m->nv;
+  d.seed_lo = (unsigned)(c->seed & 0xffffffffu); d.seed_hi = (unsigned)(c->seed >> 32);
+  d.ctrl_freq = (float)c->control_freq;
+  for (int k = 0; k < 6; k++) { d.kp[k] = (float)c->kp[k]; d.dr[k] = (float)c->damping_ratio[k]; d.out_max[k] = (float)c->output_max[k]; d.out_min[k] = (float)c->output_min[k]; }
+  d.in_max = (float)c->input_max; d.in_min = (float)c->input_min;
+  d.kp_lim[0] = (float)c->kp_limits[0]; d.kp_lim[1] = (float)c->kp_limits[1];
+  d.kp_in_max = (float)c->kp_input_max; d.kp_in_min = (float)c->kp_input_min;
+  d.tol = c->solver_tolerance > 0 ? (float)c->solver_tolerance : 1e-6f;
+  for (int k = 0; k < 3; k++) d.eef_bias[k] = (float)c->reset_eef_bias[k];
+
+#define CKH(call)                                                                                                  \
+  do {                                                                                                             \
+    cudaError_t e_ = (call);                                                                                       \
+    if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); usim_destroy(h); return -1; } \
+  } while (0)
+  size_t N = (size_t)h->n;
+  CKH(cudaMalloc((void**)&h->qpos, N * QPAD * sizeof(float)));
+  CKH(cudaMalloc((void**)&h->qvel, N * QPAD * sizeof(float)));
+  CKH(cudaMalloc((void**)&h->warm, N * QPAD * sizeof(float)));
+  CKH(cudaMalloc((void**)&h->task, N * USIM_TASK_DIM * sizeof(float)));
+  CKH(cudaMalloc((void**)&h->armbuf, N * ARMBUF * sizeof(float)));
+  CKH(cudaMalloc((void**)&h->diag, N * USIM_DIAG_DIM * sizeof(float)));
+  CKH(cudaMalloc((void**)&h->ncon, N * sizeof(int)));
+  CKH(cudaMalloc((void**)&h->geom1, N * DEV_MAXC * sizeof(int)));
+  CKH(cudaMalloc((void**)&h->geom2, N * DEV_MAXC * sizeof(int)));
+  CKH(cudaMalloc((void**)&h->cdist, N * DEV_MAXC * sizeof(float)));
+  CKH(cudaMemset(h->qpos, 0, N * QPAD * sizeof(float)));
+  CKH(cudaMemset(h->qvel, 0, N * QPAD * sizeof(float)));
+  CKH(cudaMemset(h->warm, 0, N * QPAD * sizeof(float)));
+  CKH(cudaMemset(h->armbuf, 0, N * ARMBUF * sizeof(float)));
+  CKH(cudaMemset(h->diag, 0, N * USIM_DIAG_DIM * sizeof(float)));
+  CKH(cudaMemset(h->ncon, 0, N * sizeof(int)));
+  { // task records: everything zero except DONE = 1 (must reset before stepping)
+    std::vector<float> t(N * USIM_TASK_DIM, 0.f);
+    for (size_t e = 0; e < N; e++) t[e * USIM_TASK_DIM + USIM_TS_DONE] = 1.f;
+    CKH(cudaMemcpy(h->task, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  CKH(upload(&h->part_pos, ppos)); CKH(upload(&h->part_axis, paxis)); CKH(upload(&h->iw_dof, iwd)); CKH(upload(&h->iw_body, iwb));
+  CKH(upload(&h->nbr, nbr)); CKH(upload(&h->eq_pairs, pairs)); CKH(upload(&h->nbr_pair, nbrp));
+  CKH(cudaMallocHost((void**)&h->h_act, N * USIM_MAX_ACTION * sizeof(float)));
+  CKH(cudaMallocHost((void**)&h->h_obs, N * USIM_OBS_DIM * sizeof(float)));
+  CKH(cudaMallocHost((void**)&h->h_tobs, N * USIM_OBS_DIM * sizeof(float)));
+  CKH(cudaMallocHost((void**)&h->h_rew, N * sizeof(float)));
+  CKH(cudaMallocHost((void**)&h->h_done, N));
+  CKH(cudaMalloc((void**)&h->d_act, N * USIM_MAX_ACTION * sizeof(float)));
+  CKH(cudaMalloc((void**)&h->d_obs, N * USIM_OBS_DIM * sizeof(float)));
+  CKH(cudaMalloc((void**)&h->d_tobs, N * USIM_OBS_DIM * sizeof(float)));
+  CKH(cudaMalloc((void**)&h->d_rew, N * sizeof(float)));
+  CKH(cudaMalloc((void**)&h->d_done, N));
+  CKH(cudaMalloc((void**)&h->d_resetmask, N));
+  CKH(cudaMemset(h->d_obs, 0, N * USIM_OBS_DIM * sizeof(float)));
+  CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CKH(cudaMemcpyToSymbol(dm, &h->hm, sizeof(DevModel)));
+  h->smem = sizeof(WS) * WARPS_PER_CTA;
+  CKH(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  CKH(cudaDeviceSynchronize());
+  *out = h;
+  return 0;
+}
+
+int usim_destroy(usim_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& p : h->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  void* dev[] = {h->qpos, h->qvel, h->warm, h->task, h->armbuf, h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->part_pos,
+                 h->part_axis, h->iw_dof, h->iw_body, h->nbr, h->eq_pairs, h->nbr_pair, h->d_act, h->d_obs, h->d_tobs, h->d_rew,
+                 h->d_done, h->d_resetmask};
+  for (void* p : dev) if (p) cudaFree(p);
+  void* host[] = {h->h_act, h->h_obs, h->h_tobs, h->h_rew, h->h_done};
+  for (void* p : host) if (p) cudaFreeHost(p);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+static PartTables tables(const usim_handle* h) { return PartTables{h->part_pos, h->part_axis, h->iw_dof, h->iw_body, h->nbr}; }
+
+// launches: the DevModel symbol is per-process; re-upload if another handle changed it
+static usim_handle* g_active = nullptr;
+static int activate(usim_handle* h) {
+  CK(cudaSetDevice(h->device));
+  if (g_active != h) {
+    CK(cudaMemcpyToSymbol(dm, &h->hm, sizeof(DevModel)));
+    g_active = h;
+  }
+  return 0;
+}
+
+static int launch_forward(usim_handle* h, int mode, const uint8_t* mask, const float* act, float* obs, float* rew, uint8_t* done,
+                          cudaStream_t s, bool timed) {
+  int n = h->n;
+  arm_kernel<<<(n + 63) / 64, 64, 0, s>>>(n, mode, mask, h->qpos, h->qvel, act, h->task, h->armbuf);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed && h->pending.size() >= 4096) timed = false; // bounded: caller drains with usim_kernel_time
+  if (timed) {
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, s));
+  }
+  solve_kernel<<<(n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, 32 * WARPS_PER_CTA, h->smem, s>>>(
+      n, mode, mask, h->qpos, h->qvel, h->warm, h->task, h->armbuf, tables(h), h->eq_pairs, h->nbr_pair, obs, rew, done, h->diag,
+      h->ncon, h->geom1, h->geom2, h->cdist);
+  if (timed) {
+    CK(cudaEventRecord(e1, s));
+    h->pending.emplace_back(e0, e1);
+  }
+  h->launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int usim_reset(usim_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+  if (!h) return fail("usim_reset: null handle");
+  if (activate(h)) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  reset_kernel<<<(h->n + 63) / 64, 64, 0, s>>>(h->n, mask_dev, h->qpos, h->qvel, h->warm, h->task);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return launch_forward(h, 1, mask_dev, nullptr, obs_dev, nullptr, nullptr, s, false);
+}
+
+__global__ void copy_terminal_obs(int n, const uint8_t* __restrict__ done, const float* __restrict__ obs, float* __restrict__ tobs) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * USIM_OBS_DIM) return;
+  if (done[i / USIM_OBS_DIM]) tobs[i] = obs[i];
+}
+
+int usim_step(usim_handle* h, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, float* term_obs_dev,
+              int auto_reset, void* stream) {
+  if (!h) return fail("usim_step: null handle");
+  if (!act_dev || !done_dev) return fail("usim_step: act_dev and done_dev are required");
+  if (activate(h)) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(done_dev, 0, h->n, s)); // frozen (already done) envs report done = 0 and are skipped
+  if (launch_forward(h, 0, nullptr, act_dev, obs_dev, rew_dev, done_dev, s, true)) return -1;
+  if (auto_reset) {
+    if (term_obs_dev && obs_dev) {
+      int tot = h->n * USIM_OBS_DIM;
+      copy_terminal_obs<<<(tot + 255) / 256, 256, 0, s>>>(h->n, done_dev, obs_dev, term_obs_dev);
+      h->launches += 1;
+    }
+    reset_kernel<<<(h->n + 63) / 64, 64, 0, s>>>(h->n, done_dev, h->qpos, h->qvel, h->warm, h->task);
+    h->launches += 1;
+    if (launch_forward(h, 1, done_dev, nullptr, obs_dev, nullptr, nullptr, s, false)) return -1;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int usim_step_host(usim_handle* h, const float* act, float* obs, float* rew, uint8_t* done, float* tobs, int auto_reset) {
+  if (!h) return fail("usim_step_host: null handle");
+  if (activate(h)) return -1;
+  cudaStream_t s = h->own_stream;
+  size_t N = (size_t)h->n;
+  memcpy(h->h_act, act, N * h->adim * sizeof(float));
+  CK(cudaMemcpyAsync(h->d_act, h->h_act, N * h->adim * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (usim_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, tobs ? h->d_tobs : nullptr, auto_reset, s)) return -1;
+  CK(cudaMemcpyAsync(h->h_obs, h->d_obs, N * USIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_done, h->d_done, N, cudaMemcpyDeviceToHost, s));
+  if (tobs) CK(cudaMemcpyAsync(h->h_tobs, h->d_tobs, N * USIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (obs) memcpy(obs, h->h_obs, N * USIM_OBS_DIM * sizeof(float));
+  if (rew) memcpy(rew, h->h_rew, N * sizeof(float));
+  if (done) memcpy(done, h->h_done, N);
+  if (tobs) memcpy(tobs, h->h_tobs, N * USIM_OBS_DIM * sizeof(float));
+  return 0;
+}
+
+// strided row copies between the padded internal rows and the caller's dense [n][dim] arrays
+__global__ void rows_copy(int n, int dim, int src_pitch, int dst_pitch, const float* __restrict__ src, float* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * dim) return;
+  int e = i / dim, k = i - e * dim;
+  dst[(size_t)e * dst_pitch + k] = src[(size_t)e * src_pitch + k];
+}
+static void rc(usim_handle* h, int dim, int sp, int dp, const float* src, float* dst, cudaStream_t s) {
+  int tot = h->n * dim;
+  rows_copy<<<(tot + 255) / 256, 256, 0, s>>>(h->n, dim, sp, dp, src, dst);
+  h->launches += 1;
+}
+
+int usim_get_state(usim_handle* h, float* qpos, float* qvel, float* warm, float* task, void* stream) {
+  if (!h) return fail("usim_get_state: null handle");
+  if (activate(h)) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (qpos) rc(h, h->nq, QPAD, h->nq, h->qpos, qpos, s);
+  if (qvel) rc(h, h->nv, QPAD, h->nv, h->qvel, qvel, s);
+  if (warm) rc(h, h->nv, QPAD, h->nv, h->warm, warm, s);
+  if (task) rc(h, USIM_TASK_DIM, USIM_TASK_DIM, USIM_TASK_DIM, h->task, task, s);
+  CK(cudaGetLastError());
+  return 0;
+}
+int usim_set_state(usim_handle* h, const float* qpos, const float* qvel, const float* warm, const float* task, void* stream) {
+  if (!h) return fail("usim_set_state: null handle");
+  if (activate(h)) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (qpos) rc(h, h->nq, h->nq, QPAD, qpos, h->qpos, s);
+  if (qvel) rc(h, h->nv, h->nv, QPAD, qvel, h->qvel, s);
+  if (warm) rc(h, h->nv, h->nv, QPAD, warm, h->warm, s);
+  if (task) rc(h, USIM_TASK_DIM, USIM_TASK_DIM, USIM_TASK_DIM, task, h->task, s);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int usim_get_contacts(usim_handle* h, int32_t* ncon, int32_t* g1, int32_t* g2, float* dist, void* stream) {
+  if (!h) return fail("usim_get_contacts: null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t N = (size_t)h->n;
+  if (ncon) CK(cudaMemcpyAsync(ncon, h->ncon, N * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (g1) CK(cudaMemcpyAsync(g1, h->geom1, N * DEV_MAXC * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (g2) CK(cudaMemcpyAsync(g2, h->geom2, N * DEV_MAXC * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (dist) CK(cudaMemcpyAsync(dist, h->cdist, N * DEV_MAXC * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+int usim_get_diag(usim_handle* h, float* diag, void* stream) {
+  if (!h || !diag) return fail("usim_get_diag: null argument");
+  CK(cudaMemcpyAsync(diag, h->diag, (size_t)h->n * USIM_DIAG_DIM * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int usim_num_envs(const usim_handle* h) { return h ? h->n : -1; }
+int usim_nq(const usim_handle* h) { return h ? h->nq : -1; }
+int usim_nv(const usim_handle* h) { return h ? h->nv : -1; }
+int usim_action_dim(const usim_handle* h) { return h ? h->adim : -1; }
+int64_t usim_launch_count(const usim_handle* h) { return h ? h->launches : -1; }
+
+int usim_kernel_time(usim_handle* h, int reset, double* total_ms, int64_t* launches) {
+  if (!h) return fail("usim_kernel_time: null handle");
+  for (auto& p : h->pending) {
+    CK(cudaEventSynchronize(p.second));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, p.first, p.second));
+    h->timed_ms += ms;
+    h->timed_launches += 1;
+    cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+  }
+  h->pending.clear();
+  if (total_ms) *total_ms = h->timed_ms;
+  if (launches) *launches = h->timed_launches;
+  if (reset) { h->timed_ms = 0.0; h->timed_launches = 0; }
+  return 0;
+}

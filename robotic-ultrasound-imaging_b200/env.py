@@ -1,0 +1,460 @@
+"""Host-side mirror of the reference env API over the CUDA library.
+
+Three stacked APIs, as in the reference:
+
+* :class:`BatchedUltrasound` — the native batched env (torch CUDA tensors in / out).
+* :class:`Ultrasound` + :func:`make` — robosuite-style single env
+  (``suite.make("Ultrasound", **rl_config["robosuite"])``, rl.py:38;
+  ``reset() -> OrderedDict``, ``step(a) -> (obs, reward, done, info)``).
+* :class:`GymWrapper` — robosuite ``GymWrapper`` (rl.py:38,173): flat 19-float observation.
+* :class:`UltrasoundVecEnv` — SB3 ``VecEnv``-shaped batched env with auto-reset,
+  ``terminal_observation`` and Monitor-style ``episode`` infos (rl.py:130,140).
+
+PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from collections import OrderedDict
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .abi import (DIAG_DIM, MAX_CONTACTS, OBS_DIM, TASK_DIM, PackedModel, action_bounds, action_dim, make_config)
+from .model import SceneParams, UltrasoundModel, build_model
+
+SENSOR_NAMES = (  # ultrasound.py:394-401, dims App. A.4
+    ("eef_contact_force", 3),
+    ("eef_torque", 3),
+    ("eef_vel", 3),
+    ("eef_contact_force_z_diff", 1),
+    ("eef_contact_derivative_force_z_diff", 1),
+    ("eef_vel_diff", 1),
+    ("eef_pose_diff", 7),
+)
+PROPRIO_KEY = "robot0_proprio-state"
+
+_MODEL_CACHE: Dict[bool, PackedModel] = {}
+
+
+def packed_model(soft_torso: bool = True, params: Optional[SceneParams] = None) -> PackedModel:
+    if params is not None:
+        return PackedModel(build_model(params))
+    if soft_torso not in _MODEL_CACHE:
+        _MODEL_CACHE[soft_torso] = PackedModel(build_model(SceneParams(soft_torso=soft_torso)))
+    return _MODEL_CACHE[soft_torso]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedUltrasound:
+    """N independent Ultrasound envs stepped by one C-ABI call on one GPU."""
+
+    def __init__(
+        self,
+        num_envs: int,
+        device: int | str | torch.device = 0,
+        soft_torso: bool = True,
+        controller_configs: Optional[Dict[str, Any]] = None,
+        control_freq: float = 500,
+        horizon: int = 1000,
+        early_termination: bool = False,
+        torso_solref_randomization: bool = False,
+        initial_probe_pos_randomization: bool = False,
+        deterministic_trajectory: bool = False,
+        seed: int = 0,
+        env_id_offset: int = 0,
+        solver_iterations: int = 40,
+        solver_tolerance: float = 1e-6,
+        scene_params: Optional[SceneParams] = None,
+        **cfg_kwargs,
+    ):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedUltrasound needs a CUDA device: the env step has no CPU fallback")
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        self.packed = packed_model(soft_torso, scene_params)
+        self.model: UltrasoundModel = self.packed.model
+        self.cfg = make_config(
+            num_envs, controller_configs, control_freq=control_freq, horizon=horizon, early_termination=early_termination,
+            torso_solref_randomization=torso_solref_randomization, initial_probe_pos_randomization=initial_probe_pos_randomization,
+            deterministic_trajectory=deterministic_trajectory, seed=seed, env_id_offset=env_id_offset,
+            solver_iterations=solver_iterations, solver_tolerance=solver_tolerance, **cfg_kwargs)
+        self.num_envs = int(num_envs)
+        self.nq, self.nv = self.model.nq, self.model.nv
+        self.action_dim = action_dim(self.cfg)
+        self.horizon = int(horizon)
+        self.control_freq = float(control_freq)
+        L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(L.usim_create(C.byref(self.packed.struct), C.byref(self.cfg), self.device.index or 0, C.byref(h)))
+        self._h = h
+        N, dev = self.num_envs, self.device
+        self.obs = torch.zeros(N, OBS_DIM, device=dev)
+        self.term_obs = torch.zeros(N, OBS_DIM, device=dev)
+        self.rew = torch.zeros(N, device=dev)
+        self.done = torch.zeros(N, dtype=torch.uint8, device=dev)
+
+    # -- lifecycle ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().usim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def action_spec(self):
+        return action_bounds(self.cfg)
+
+    # -- core --------------------------------------------------------------
+    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().usim_reset(self._h, _ptr(mask), _ptr(self.obs), self._stream()))
+        return self.obs
+
+    def step(self, actions: torch.Tensor, auto_reset: bool = True):
+        a = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        assert a.shape == (self.num_envs, self.action_dim), a.shape
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().usim_step(self._h, _ptr(a), _ptr(self.obs), _ptr(self.rew), _ptr(self.done), _ptr(self.term_obs),
+                                            int(auto_reset), self._stream()))
+        return self.obs, self.rew, self.done, self.term_obs
+
+    def step_host(self, actions: np.ndarray, auto_reset: bool = True):
+        """End-to-end call with HOST buffers (copies inside the library)."""
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        assert a.shape == (self.num_envs, self.action_dim), a.shape
+        if not hasattr(self, "_h_obs"):
+            N = self.num_envs
+            self._h_obs, self._h_tobs = np.zeros((N, OBS_DIM), np.float32), np.zeros((N, OBS_DIM), np.float32)
+            self._h_rew, self._h_done = np.zeros(N, np.float32), np.zeros(N, np.uint8)
+        p = lambda x: C.c_void_p(x.ctypes.data)
+        _lib.check(_lib.lib().usim_step_host(self._h, p(a), p(self._h_obs), p(self._h_rew), p(self._h_done), p(self._h_tobs), int(auto_reset)))
+        return self._h_obs, self._h_rew, self._h_done, self._h_tobs
+
+    # -- parity hooks --------------------------------------------------------
+    def get_state(self):
+        N, dev = self.num_envs, self.device
+        q, v, w = torch.empty(N, self.nq, device=dev), torch.empty(N, self.nv, device=dev), torch.empty(N, self.nv, device=dev)
+        t = torch.empty(N, TASK_DIM, device=dev)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().usim_get_state(self._h, _ptr(q), _ptr(v), _ptr(w), _ptr(t), self._stream()))
+        return q, v, w, t
+
+    def set_state(self, qpos=None, qvel=None, warm=None, task=None):
+        def prep(x, d):
+            if x is None:
+                return None
+            x = torch.as_tensor(x, dtype=torch.float32, device=self.device).contiguous()
+            assert x.shape == (self.num_envs, d), (x.shape, d)
+            return x
+
+        q, v, w, t = prep(qpos, self.nq), prep(qvel, self.nv), prep(warm, self.nv), prep(task, TASK_DIM)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().usim_set_state(self._h, _ptr(q), _ptr(v), _ptr(w), _ptr(t), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()  # inputs may be temporaries
+
+    def contacts(self):
+        N, dev = self.num_envs, self.device
+        ncon = torch.empty(N, dtype=torch.int32, device=dev)
+        g1 = torch.empty(N, MAX_CONTACTS, dtype=torch.int32, device=dev)
+        g2 = torch.empty(N, MAX_CONTACTS, dtype=torch.int32, device=dev)
+        dist = torch.empty(N, MAX_CONTACTS, device=dev)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().usim_get_contacts(self._h, _ptr(ncon), _ptr(g1), _ptr(g2), _ptr(dist), self._stream()))
+        return ncon, g1, g2, dist
+
+    def diag(self):
+        d = torch.empty(self.num_envs, DIAG_DIM, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().usim_get_diag(self._h, _ptr(d), self._stream()))
+        return d
+
+    @property
+    def launch_count(self) -> int:
+        return int(_lib.lib().usim_launch_count(self._h))
+
+    def kernel_time(self, reset: bool = True):
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(_lib.lib().usim_kernel_time(self._h, int(reset), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+# ----------------------------------------------------------------------------
+# robosuite-style single env
+# ----------------------------------------------------------------------------
+class _Robot:
+    """The slice of robosuite's robot object the task code reads."""
+
+    def __init__(self, env: "Ultrasound"):
+        self._env = env
+        self.name = "Panda"
+        self.dof = 7
+        self.init_qpos = np.array(env.core.model.params.init_qpos)
+
+    @property
+    def action_dim(self):
+        return self._env.core.action_dim
+
+    @property
+    def _joint_positions(self):
+        return self._env.core.get_state()[0][0, :7].cpu().numpy().astype(np.float64)
+
+    @property
+    def torques(self):
+        return self._env.core.diag()[0, 13:20].cpu().numpy().astype(np.float64)
+
+    @property
+    def ee_torque(self):
+        return self._env.core.diag()[0, 3:6].cpu().numpy().astype(np.float64)
+
+
+class Ultrasound:
+    """robosuite-style ``Ultrasound`` env (kwargs of ultrasound.py:99-133)."""
+
+    def __init__(
+        self,
+        robots="Panda",
+        env_configuration="default",
+        controller_configs=None,
+        gripper_types="UltrasoundProbeGripper",
+        initialization_noise="default",
+        table_full_size=(0.8, 0.8, 0.05),
+        table_friction=100 * (1.0, 5e-3, 1e-4),
+        use_camera_obs=False,
+        use_object_obs=True,
+        reward_scale=1.0,
+        reward_shaping=False,
+        placement_initializer=None,
+        has_renderer=False,
+        has_offscreen_renderer=False,
+        render_camera="frontview",
+        render_collision_mesh=False,
+        render_visual_mesh=True,
+        render_gpu_device_id=-1,
+        control_freq=20,
+        horizon=1000,
+        ignore_done=False,
+        hard_reset=True,
+        camera_names="agentview",
+        camera_heights=256,
+        camera_widths=256,
+        camera_depths=False,
+        early_termination=False,
+        save_data=False,
+        deterministic_trajectory=False,
+        torso_solref_randomization=False,
+        initial_probe_pos_randomization=False,
+        use_box_torso=True,
+        seed=0,
+        device=0,
+        soft_torso=True,
+    ):
+        assert gripper_types == "UltrasoundProbeGripper", "Tried to specify gripper other than UltrasoundProbeGripper in Ultrasound environment!"
+        assert robots == "Panda", "Only the Panda arm is built in this round (UR5e: SURVEY §8f rank 2)"
+        assert use_box_torso, "Only the box torso is built in this round (cylinder torso: SURVEY §8f rank 2)"
+        if use_camera_obs or has_renderer or has_offscreen_renderer:
+            raise NotImplementedError("rendering / camera observations are out of scope of the hot path (SURVEY §2.1 #4, §8f rank 4)")
+        if save_data:
+            raise NotImplementedError("save_data CSV stream is a later row (SURVEY §8f rank 3)")
+        self.use_camera_obs, self.use_object_obs = use_camera_obs, use_object_obs
+        self.reward_scale, self.reward_shaping = reward_scale, reward_shaping
+        self.horizon, self.control_freq = horizon, control_freq
+        self.control_timestep = 1.0 / control_freq
+        self.ignore_done = ignore_done
+        self.early_termination = early_termination
+        self.core = BatchedUltrasound(
+            1, device=device, soft_torso=soft_torso, controller_configs=controller_configs, control_freq=control_freq,
+            horizon=horizon, early_termination=early_termination, torso_solref_randomization=torso_solref_randomization,
+            initial_probe_pos_randomization=initial_probe_pos_randomization, deterministic_trajectory=deterministic_trajectory,
+            seed=seed)
+        self.robots = [_Robot(self)]
+        self.timestep = 0
+        self.done = True
+
+    @property
+    def action_spec(self):
+        return self.core.action_spec
+
+    @property
+    def action_dim(self):
+        return self.core.action_dim
+
+    def _obs_dict(self, flat: np.ndarray) -> "OrderedDict[str, np.ndarray]":
+        od: "OrderedDict[str, np.ndarray]" = OrderedDict()
+        k = 0
+        for name, dim in SENSOR_NAMES:
+            od[name] = flat[k : k + dim].copy()
+            k += dim
+        od[PROPRIO_KEY] = flat.copy()
+        return od
+
+    def reset(self):
+        flat = self.core.reset()[0].cpu().numpy().astype(np.float64)
+        self.timestep, self.done = 0, False
+        return self._obs_dict(flat)
+
+    def step(self, action):
+        if self.done:
+            raise ValueError("executing action in terminated episode")
+        a = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, -1))
+        obs, rew, done, _ = self.core.step(a, auto_reset=False)
+        self.timestep += 1
+        d = bool(done[0].item()) and not self.ignore_done
+        self.done = d
+        return self._obs_dict(obs[0].cpu().numpy().astype(np.float64)), float(rew[0].item()), d, {}
+
+    def _check_probe_contact_with_torso(self) -> bool:
+        """ultrasound.py:714-736: any active contact between probe_collision and a geom named G\\d+_\\d+_\\d+."""
+        import re
+
+        ncon, g1, g2, _ = self.core.contacts()
+        n = int(ncon[0].item())
+        names = self.core.model
+        for a, b in zip(g1[0, :n].tolist(), g2[0, :n].tolist()):
+            n1, n2 = names.geom_name(a), names.geom_name(b)
+            if "probe_collision" in n1 or "probe_collision" in n2:
+                if re.search(r"[G]\d+[_]\d+[_]\d+$", n1) or re.search(r"[G]\d+[_]\d+[_]\d+$", n2):
+                    return True
+        return False
+
+    def close(self):
+        self.core.close()
+
+
+_REGISTERED = {"Ultrasound": Ultrasound}
+
+
+def make(env_name: str, *args, **kwargs):
+    """``robosuite.make`` for the one env this framework provides."""
+    if env_name not in _REGISTERED:
+        raise Exception(f"Environment {env_name} not found. Registered: {', '.join(_REGISTERED)}")
+    return _REGISTERED[env_name](*args, **kwargs)
+
+
+class _Box:
+    """Minimal ``gym.spaces.Box`` stand-in (gym is not a dependency)."""
+
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        self.low = np.broadcast_to(np.asarray(low, dtype=dtype), shape if shape is not None else np.shape(low)).copy()
+        self.high = np.broadcast_to(np.asarray(high, dtype=dtype), self.low.shape).copy()
+        self.shape, self.dtype = self.low.shape, np.dtype(dtype)
+
+    def sample(self, rng: Optional[np.random.Generator] = None):
+        rng = rng or np.random.default_rng()
+        return rng.uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+    def __repr__(self):
+        return f"Box({self.low.min()}, {self.high.max()}, {self.shape}, {self.dtype})"
+
+
+class GymWrapper:
+    """robosuite ``GymWrapper``: flattens ``keys`` (default: the proprio modality) into one vector."""
+
+    def __init__(self, env: Ultrasound, keys: Optional[Sequence[str]] = None):
+        self.env = env
+        self.keys = list(keys) if keys is not None else [PROPRIO_KEY]
+        self.name = "Panda_" + type(env).__name__
+        self.reward_range = (0, env.reward_scale)
+        low, high = env.action_spec
+        self.action_space = _Box(low.astype(np.float32), high.astype(np.float32))
+        self.obs_dim = sum(dict(SENSOR_NAMES, **{PROPRIO_KEY: OBS_DIM})[k] for k in self.keys)
+        self.observation_space = _Box(-np.inf, np.inf, (self.obs_dim,), np.float32)
+
+    def _flatten_obs(self, obs_dict):
+        return np.concatenate([np.asarray(obs_dict[k]).flatten() for k in self.keys])
+
+    def reset(self):
+        return self._flatten_obs(self.env.reset())
+
+    def step(self, action):
+        od, reward, done, info = self.env.step(action)
+        return self._flatten_obs(od), reward, done, info
+
+    def seed(self, seed=None):
+        if seed is not None:
+            np.random.seed(seed)
+
+    def close(self):
+        self.env.close()
+
+
+class UltrasoundVecEnv:
+    """SB3 ``VecEnv``-shaped batched env (SubprocVecEnv + Monitor semantics, rl.py:36-41,130)."""
+
+    def __init__(self, num_envs: int, env_options: Optional[Dict[str, Any]] = None, seed: int = 0, device=0, env_id_offset: int = 0):
+        opts = dict(env_options or {})
+        for k in ("env_id", "robots", "use_camera_obs", "use_object_obs", "has_renderer", "has_offscreen_renderer", "render_camera",
+                  "camera_names", "camera_heights", "camera_widths", "camera_depths", "reward_shaping", "save_data", "use_box_torso",
+                  "gripper_types"):
+            opts.pop(k, None)
+        self.core = BatchedUltrasound(num_envs, device=device, seed=seed, env_id_offset=env_id_offset, **opts)
+        self.num_envs = num_envs
+        low, high = self.core.action_spec
+        self.action_space = _Box(low.astype(np.float32), high.astype(np.float32))
+        self.observation_space = _Box(-np.inf, np.inf, (OBS_DIM,), np.float32)
+        self._actions = None
+        self._t0 = time.time()
+        self._ep_ret = np.zeros(num_envs, np.float64)
+        self._ep_len = np.zeros(num_envs, np.int64)
+
+    def reset(self) -> np.ndarray:
+        self._ep_ret[:] = 0
+        self._ep_len[:] = 0
+        return self.core.reset().cpu().numpy()
+
+    def step_async(self, actions):
+        self._actions = np.clip(np.asarray(actions, dtype=np.float32), self.action_space.low, self.action_space.high)
+
+    def step_wait(self):
+        obs, rew, done, tobs = self.core.step_host(self._actions, auto_reset=True)
+        obs, rew, done = obs.copy(), rew.copy(), done.astype(bool)
+        self._ep_ret += rew
+        self._ep_len += 1
+        infos: List[Dict[str, Any]] = [{} for _ in range(self.num_envs)]
+        for i in np.nonzero(done)[0]:
+            infos[i]["terminal_observation"] = tobs[i].copy()
+            infos[i]["episode"] = {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": round(time.time() - self._t0, 6)}
+            self._ep_ret[i] = 0
+            self._ep_len[i] = 0
+        return obs, rew, done, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        self.core.close()
+
+    def seed(self, seed=None):
+        return [None] * self.num_envs
+
+    def get_attr(self, name, indices=None):
+        return [getattr(self.core, name)] * self.num_envs
+
+    def set_attr(self, name, value, indices=None):
+        raise NotImplementedError("per-env attributes are fixed at construction")
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        raise NotImplementedError(method_name)
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False] * self.num_envs
