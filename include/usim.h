@@ -196,6 +196,9 @@ int usim_kernel_time(usim_handle* h, int reset, double* total_ms, int64_t* launc
 
 const char* usim_last_error(void);
 int usim_abi_version(void);
+/* sizeof(usim_model) / sizeof(usim_config) as compiled, so that bindings can validate their struct mirrors */
+size_t usim_sizeof_model(void);
+size_t usim_sizeof_config(void);
 
 #ifdef __cplusplus
 }

@@ -1191,12 +1191,8 @@ void oracle_reset(oracle_env* e, double* obs) {
     memcpy(ts + USIM_TS_TRAJ_START, s, sizeof s); memcpy(ts + USIM_TS_TRAJ_END, en, sizeof en);
   } else {
     oracle_philox(c->seed, (uint32_t)e->gid, ep, 1, 0, r);
-    double x0 = -0.15 + tx + 0.03, x1 = 0.15 + tx, y0 = -0.09 + ty, y1 = 0.09 + ty;
-    for (int w = 0; w < 2; w++) {
-      ts[(w ? USIM_TS_TRAJ_END : USIM_TS_TRAJ_START) + 0] = x0 + (x1 - x0) * (double)(r[2 * w] % 50u) / 49.0;
-      ts[(w ? USIM_TS_TRAJ_END : USIM_TS_TRAJ_START) + 1] = y0 + (y1 - y0) * (double)(r[2 * w + 1] % 50u) / 49.0;
-      ts[(w ? USIM_TS_TRAJ_END : USIM_TS_TRAJ_START) + 2] = tz + 0.039;
-    }
+    oracle_grid_point(tx, ty, tz, (int)(r[0] % 50u), (int)(r[1] % 50u), ts + USIM_TS_TRAJ_START);
+    oracle_grid_point(tx, ty, tz, (int)(r[2] % 50u), (int)(r[3] % 50u), ts + USIM_TS_TRAJ_END);
   }
   oracle_philox(c->seed, (uint32_t)e->gid, ep, 2, 0, r);
   ts[USIM_TS_U0] = u01(r[0]); /* ultrasound.py:443 (unseeded in the reference) */
@@ -1253,26 +1249,38 @@ int oracle_step(oracle_env* e, const double* action, double* obs, double* reward
     integrate(e);
   }
   hand_velocity(e);
-  /* _post_action: reward first, with the task state of the previous step (ultrasound.py:525) */
-  int in_contact = e->in_contact;
+  oracle_post_action(ts, c->horizon, c->control_freq, c->early_termination, m->jnt_range, e->eef_pos, e->eef_quat, e->hand_vel,
+                     e->cfrc[2], e->in_contact, e->qpos, reward, done);
+  write_obs(e, obs);
+  return 0;
+}
+
+/* Ultrasound._post_action (ultrasound.py:512-550) with reward (:230-269) and _check_terminated (:635-670); pure:
+ * reads the post-physics measurements, updates the task record `ts` in place (timestep already incremented). */
+void oracle_post_action(double* ts, int horizon, double control_freq, int early_termination, const double* jnt_range,
+                        const double* eef_pos, const double* eef_quat_xyzw, const double* hand_vel, double fz, int in_contact,
+                        const double* qpos7, double* reward, int* done) {
+  /* reward first, with the task state of the previous step (:525); the contact query latches has_touched_torso (:733) */
   if (in_contact) ts[USIM_TS_TOUCHED] = 1;
   double pe[2], oe;
-  *reward = oracle_reward(e->eef_pos, e->eef_quat, ts + USIM_TS_TRAJ_PT, ts[USIM_TS_VEL_MEAN], ts[USIM_TS_FZ_MEAN],
-                          ts[USIM_TS_DFZ], in_contact, pe, &oe);
+  *reward = oracle_reward(eef_pos, eef_quat_xyzw, ts + USIM_TS_TRAJ_PT, ts[USIM_TS_VEL_MEAN], ts[USIM_TS_FZ_MEAN], ts[USIM_TS_DFZ],
+                          in_contact, pe, &oe);
   ts[USIM_TS_POS_ERR] = pe[0]; ts[USIM_TS_POS_ERR + 1] = pe[1]; ts[USIM_TS_ORI_ERR] = oe;
   ts[USIM_TS_IN_CONTACT] = in_contact;
-  int dn = ts[USIM_TS_TIMESTEP] >= c->horizon;
   double t = ts[USIM_TS_TIMESTEP];
-  traj_eval(e, t / (double)c->horizon + ts[USIM_TS_U0], ts + USIM_TS_TRAJ_PT); /* :528-532, two waypoints */
-  ts[USIM_TS_VEL_MEAN] += (norm3(e->hand_vel) - ts[USIM_TS_VEL_MEAN]) / t;         /* :538 */
-  double fz = e->cfrc[2];
-  ts[USIM_TS_DFZ] = (fz - ts[USIM_TS_FZ_PREV]) / (1.0 / c->control_freq);          /* :542 */
+  int dn = t >= horizon;
+  double u = t / (double)horizon + ts[USIM_TS_U0]; /* :528-532, two waypoints; klampt eval clamps ("halt") */
+  u = u < 0 ? 0 : (u > 1 ? 1 : u);
+  for (int k = 0; k < 3; k++) ts[USIM_TS_TRAJ_PT + k] = ts[USIM_TS_TRAJ_START + k] + u * (ts[USIM_TS_TRAJ_END + k] - ts[USIM_TS_TRAJ_START + k]);
+  ts[USIM_TS_VEL_MEAN] += (norm3(hand_vel) - ts[USIM_TS_VEL_MEAN]) / t;     /* :538 */
+  ts[USIM_TS_DFZ] = (fz - ts[USIM_TS_FZ_PREV]) / (1.0 / control_freq);      /* :542 */
   ts[USIM_TS_FZ_PREV] = fz;
-  ts[USIM_TS_FZ_MEAN] = 0.1 * fz + 0.9 * ts[USIM_TS_FZ_MEAN];                      /* :546 */
-  if (c->early_termination) { /* :635-670 */
+  ts[USIM_TS_FZ_MEAN] = 0.1 * fz + 0.9 * ts[USIM_TS_FZ_MEAN];               /* :546 */
+  if (early_termination) { /* :635-670 */
     int term = 0;
-    for (int j = 0; j < 7; j++) /* robosuite check_q_limits, tolerance 0.1 */
-      if (!(m->jnt_range[2 * j] + 0.1 < e->qpos[j] && e->qpos[j] < m->jnt_range[2 * j + 1] - 0.1)) term = 1;
+    if (qpos7)
+      for (int j = 0; j < 7; j++) /* robosuite check_q_limits, tolerance 0.1 */
+        if (!(jnt_range[2 * j] + 0.1 < qpos7[j] && qpos7[j] < jnt_range[2 * j + 1] - 0.1)) term = 1;
     if (sqrt(pe[0] * pe[0] + pe[1] * pe[1]) > 1.0) term = 1;
     if (in_contact && oe > 0.10) term = 1;
     if (ts[USIM_TS_TOUCHED] != 0 && !in_contact) term = 1;
@@ -1280,8 +1288,14 @@ int oracle_step(oracle_env* e, const double* action, double* obs, double* reward
   }
   ts[USIM_TS_DONE] = dn;
   *done = dn;
-  write_obs(e, obs);
-  return 0;
+}
+
+/* waypoint grid of get_trajectory (ultrasound.py:787-788,805-807): value of grid index i in [0,50) */
+void oracle_grid_point(double tx, double ty, double tz, int ix, int iy, double* pt) {
+  double x0 = -0.15 + tx + 0.03, x1 = 0.15 + tx, y0 = -0.09 + ty, y1 = 0.09 + ty;
+  pt[0] = x0 + (x1 - x0) * (double)ix / 49.0;
+  pt[1] = y0 + (y1 - y0) * (double)iy / 49.0;
+  pt[2] = tz + 0.039;
 }
 
 /* ------------------------------------------------------------------ state access / introspection */

@@ -69,6 +69,10 @@ void oracle_difference_quat(const double* q1, const double* q2, double* out);
 void oracle_mat2quat_xyzw(const double* mat9, double* q);
 double oracle_reward(const double* eef_pos, const double* eef_quat_xyzw, const double* traj_pt, double vel_mean,
                      double fz_mean, double dfz, int in_contact, double* pos_err2, double* ori_err);
+void oracle_post_action(double* ts, int horizon, double control_freq, int early_termination, const double* jnt_range,
+                        const double* eef_pos, const double* eef_quat_xyzw, const double* hand_vel, double fz, int in_contact,
+                        const double* qpos7, double* reward, int* done);
+void oracle_grid_point(double tx, double ty, double tz, int ix, int iy, double* pt);
 void oracle_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out4);
 
 /* batched rollouts for the CPU baseline: n envs, OpenMP over envs.

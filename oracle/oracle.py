@@ -64,6 +64,8 @@ def lib():
         L.oracle_mat2quat_xyzw.argtypes = [_pd, _pd]
         L.oracle_reward.restype = C.c_double
         L.oracle_reward.argtypes = [_pd, _pd, _pd, C.c_double, C.c_double, C.c_double, C.c_int, _pd, _pd]
+        L.oracle_post_action.argtypes = [_pd, C.c_int, C.c_double, C.c_int, _pd, _pd, _pd, _pd, C.c_double, C.c_int, _pd, _pd, _pi]
+        L.oracle_grid_point.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, _pd]
         L.oracle_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.oracle_rollout.restype = C.c_long
         L.oracle_rollout.argtypes = [C.POINTER(C.c_void_p), C.c_int, _pd, C.c_int, C.c_int, C.c_int, C.c_int, _pd]
@@ -229,6 +231,24 @@ def reward(eef_pos, eef_quat_xyzw, traj_pt, vel_mean, fz_mean, dfz, in_contact):
     r = lib().oracle_reward(_p(_f64(eef_pos, 3)), _p(_f64(eef_quat_xyzw, 4)), _p(_f64(traj_pt, 3)), float(vel_mean),
                             float(fz_mean), float(dfz), int(bool(in_contact)), _p(pe), C.byref(oe))
     return r, pe, oe.value
+
+
+def post_action(ts, horizon, control_freq, early_termination, jnt_range, eef_pos, eef_quat_xyzw, hand_vel, fz, in_contact, qpos7=None):
+    """In-place update of the task record ``ts`` (float64[TASK_DIM]); returns (reward, done)."""
+    assert ts.dtype == np.float64 and ts.size == TASK_DIM
+    rew, done = C.c_double(), C.c_int()
+    jr = _f64(jnt_range, 14)
+    q = None if qpos7 is None else _f64(qpos7, 7)
+    lib().oracle_post_action(_p(ts), int(horizon), float(control_freq), int(bool(early_termination)), _p(jr), _p(_f64(eef_pos, 3)),
+                             _p(_f64(eef_quat_xyzw, 4)), _p(_f64(hand_vel, 3)), float(fz), int(bool(in_contact)),
+                             None if q is None else _p(q), C.byref(rew), C.byref(done))
+    return rew.value, bool(done.value)
+
+
+def grid_point(torso_xpos, ix, iy):
+    out = np.zeros(3)
+    lib().oracle_grid_point(float(torso_xpos[0]), float(torso_xpos[1]), float(torso_xpos[2]), int(ix), int(iy), _p(out))
+    return out
 
 
 def philox(seed, c0, c1, c2, c3):

@@ -35,6 +35,8 @@ SYMBOLS = {
     "usim_kernel_time": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "usim_last_error": (C.c_char_p, []),
     "usim_abi_version": (C.c_int, []),
+    "usim_sizeof_model": (C.c_size_t, []),
+    "usim_sizeof_config": (C.c_size_t, []),
 }
 
 

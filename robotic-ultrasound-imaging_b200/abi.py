@@ -18,6 +18,8 @@ TASK_DIM = 48
 MAX_CONTACTS = 160
 DIAG_DIM = 24
 
+GOAL_QUAT_XYZW = (-0.69192486, 0.72186726, -0.00514253, -0.01100909)  # ultrasound.py:174
+
 MODE_FIXED, MODE_TRACKING, MODE_VARIABLE_Z, MODE_WRENCH = 0, 1, 2, 3
 MODE_BY_NAME = {"fixed": MODE_FIXED, "tracking": MODE_TRACKING, "variable_z": MODE_VARIABLE_Z, "wrench": MODE_WRENCH}
 

@@ -650,7 +650,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
   int iters = 0;
   const int maxit = mode == 1 ? 2 * dm.iters : dm.iters;
   for (int it = 0; it < maxit; it++) {
-    if (gnorm <= dm.tol * (1.f + rhsn)) break;
+    // fp32 floor of the gradient is ~eps * (|Hx| + |rhs|): the terms that cancel in it
+    if (gnorm <= dm.tol * (1.f + rhsn + sqrtf(vdot(w.Hx, w.Hx)))) break;
     iters = it + 1;
     applyH(w.s, w.hs);
     dense_vel(w.s);

@@ -50,6 +50,8 @@ struct usim_handle {
 
 const char* usim_last_error(void) { return g_err.c_str(); }
 int usim_abi_version(void) { return USIM_ABI_VERSION; }
+size_t usim_sizeof_model(void) { return sizeof(usim_model); }
+size_t usim_sizeof_config(void) { return sizeof(usim_config); }
 
 template <typename T>
 static cudaError_t upload(T** dst, const std::vector<T>& v) {

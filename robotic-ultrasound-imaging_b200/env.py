@@ -15,6 +15,7 @@ PyTorch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes as C
+import re
 import time
 from collections import OrderedDict
 from typing import Any, Dict, List, Optional, Sequence
@@ -36,6 +37,18 @@ SENSOR_NAMES = (  # ultrasound.py:394-401, dims App. A.4
     ("eef_pose_diff", 7),
 )
 PROPRIO_KEY = "robot0_proprio-state"
+
+_TORSO_GEOM_RE = re.compile(r"[G]\d+[_]\d+[_]\d+$")  # ultrasound.py:724
+
+
+def probe_torso_contact(name_pairs, probe_geoms=("gripper0_probe_collision",)) -> bool:
+    """ultrasound.py:673-736 on a list of (geom1 name, geom2 name) of the active contacts."""
+    for n1, n2 in name_pairs:
+        if n1 in probe_geoms or n2 in probe_geoms:
+            if _TORSO_GEOM_RE.search(n1) is not None or _TORSO_GEOM_RE.search(n2) is not None:
+                return True
+    return False
+
 
 _MODEL_CACHE: Dict[bool, PackedModel] = {}
 
@@ -320,17 +333,10 @@ class Ultrasound:
 
     def _check_probe_contact_with_torso(self) -> bool:
         """ultrasound.py:714-736: any active contact between probe_collision and a geom named G\\d+_\\d+_\\d+."""
-        import re
-
         ncon, g1, g2, _ = self.core.contacts()
         n = int(ncon[0].item())
         names = self.core.model
-        for a, b in zip(g1[0, :n].tolist(), g2[0, :n].tolist()):
-            n1, n2 = names.geom_name(a), names.geom_name(b)
-            if "probe_collision" in n1 or "probe_collision" in n2:
-                if re.search(r"[G]\d+[_]\d+[_]\d+$", n1) or re.search(r"[G]\d+[_]\d+[_]\d+$", n2):
-                    return True
-        return False
+        return probe_torso_contact([(names.geom_name(a), names.geom_name(b)) for a, b in zip(g1[0, :n].tolist(), g2[0, :n].tolist())])
 
     def close(self):
         self.core.close()

@@ -1,0 +1,161 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol include/usim.h declares,
+the ctypes struct mirrors match the compiled structs, the config mapping follows rl_config.yaml, the model
+builder reproduces the composite numbers of SURVEY App. B, and the product path fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import CC_FIXED, CC_TRACK, ROOT
+from rui_b200 import _lib, abi
+from rui_b200.model import SceneParams, build_model
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "usim.h")).read()
+    declared = set(re.findall(r"\b(usim_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    L = _lib.lib()
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert L.usim_abi_version() == abi.USIM_ABI_VERSION
+
+
+def test_struct_mirrors_match_compiled_layout():
+    L = _lib.lib()
+    assert L.usim_sizeof_model() == ctypes.sizeof(abi.UsimModel)
+    assert L.usim_sizeof_config() == ctypes.sizeof(abi.UsimConfig)
+    hdr = open(os.path.join(ROOT, "include", "usim.h")).read()
+    assert int(re.search(r"#define USIM_TASK_DIM (\d+)", hdr).group(1)) == abi.TASK_DIM
+    assert int(re.search(r"#define USIM_MAX_CONTACTS (\d+)", hdr).group(1)) == abi.MAX_CONTACTS
+    assert int(re.search(r"#define USIM_OBS_DIM (\d+)", hdr).group(1)) == abi.OBS_DIM
+    assert int(re.search(r"#define USIM_DIAG_DIM (\d+)", hdr).group(1)) == abi.DIAG_DIM
+    for name, val in re.findall(r"(USIM_TS_[A-Z_]+) = (\d+)", hdr):
+        py = name.replace("USIM_", "")
+        if hasattr(abi, py):
+            assert getattr(abi, py) == int(val), name
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from rui_b200.env import BatchedUltrasound, UltrasoundVecEnv, make
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BatchedUltrasound(4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        UltrasoundVecEnv(2, dict(controller_configs=CC_TRACK, control_freq=500))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        make("Ultrasound", robots="Panda", controller_configs=CC_TRACK, control_freq=500)
+    # the C entry point itself refuses too
+    from rui_b200.env import packed_model
+    pk = packed_model(False)
+    cfg = abi.make_config(2, CC_FIXED, control_freq=500)
+    h = ctypes.c_void_p()
+    rc = _lib.lib().usim_create(ctypes.byref(pk.struct), ctypes.byref(cfg), 0, ctypes.byref(h))
+    assert rc != 0 and b"no CUDA device" in _lib.lib().usim_last_error()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "robotic-ultrasound-imaging_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                for pat in (r"^\s*(from|import)\s+oracle", r"liboracle", r"#include\s+\"[^\"]*oracle", r"import_module\([^)]*oracle", r"oracle/"):
+                    assert re.search(pat, src, re.M) is None, (f, pat)
+    assert "#include" not in open(os.path.join(ROOT, "include", "usim.h")).read().replace("#include <stddef.h>", "").replace("#include <stdint.h>", "")
+
+
+def test_config_mapping_follows_rl_config_yaml():
+    import yaml
+    cfg_yaml = yaml.safe_load("""
+      type: "OSC_POSE"
+      input_max: 1
+      input_min: -1
+      output_max: [0.05, 0.05, 0.05, 0.5, 0.5, 0.5]
+      output_min: [-0.05, -0.05, -0.05, -0.5, -0.5, -0.5]
+      kp: 300
+      damping_ratio: 1
+      impedance_mode: "tracking"
+      kp_limits: [0, 500]
+      kp_input_max: 1
+      kp_input_min: 0
+      damping_ratio_limits: [0, 2]
+      position_limits: null
+      orientation_limits: null
+      uncouple_pos_ori: True
+      control_delta: True
+      interpolation: null
+      ramp_ratio: 0.2
+    """)
+    c = abi.make_config(64, cfg_yaml, control_freq=500, horizon=1000, early_termination=True, torso_solref_randomization=True,
+                        initial_probe_pos_randomization=True, seed=3)
+    assert c.impedance_mode == abi.MODE_TRACKING and abi.action_dim(c) == 6
+    lo, hi = abi.action_bounds(c)
+    assert lo.tolist() == [0] * 6 and hi.tolist() == [1] * 6  # [ART] action space of tracking.zip
+    assert list(c.kp) == [300] * 6 and list(c.kp_limits) == [0, 500] and c.uncouple_pos_ori == 1
+    assert c.early_termination == 1 and c.solref_randomization == 1 and c.probe_pos_randomization == 1 and c.seed == 3
+    c2 = abi.make_config(1, dict(cfg_yaml, impedance_mode="variable_z"), control_freq=500)
+    lo, hi = abi.action_bounds(c2)
+    assert abi.action_dim(c2) == 7 and lo[-1] == -1 and hi[-1] == 1
+    lo, hi = abi.action_bounds(abi.make_config(1, dict(cfg_yaml, impedance_mode="wrench"), control_freq=500))
+    assert lo.tolist() == [-10] * 6 and hi.tolist() == [10] * 6
+    lo, hi = abi.action_bounds(abi.make_config(1, dict(cfg_yaml, impedance_mode="fixed"), control_freq=500))
+    assert lo.tolist() == [-1] * 6 and hi.tolist() == [1] * 6
+    with pytest.raises(AssertionError):
+        abi.make_config(1, dict(cfg_yaml, type="JOINT_POSITION"))
+
+
+def test_art_action_spaces_match(art):
+    for model, mode in (("tracking", "tracking"), ("variable_z", "variable_z"), ("wrench", "wrench")):
+        lo, hi = abi.action_bounds(abi.make_config(1, dict(CC_TRACK, impedance_mode=mode), control_freq=500))
+        np.testing.assert_allclose(lo, art[model]["action_low"])
+        np.testing.assert_allclose(hi, art[model]["action_high"])
+
+
+def test_composite_numbers(soft_model):
+    m = soft_model.model
+    assert (m.nq, m.nv, m.nbody) == (284, 283, 282)
+    assert len(m.part_pos) == 270 and len(m.eq_pairs) == 536  # App. B.2
+    pos = m.part_pos
+    np.testing.assert_allclose(np.abs(pos).max(axis=0), [0.14, 0.0525, 0.175])
+    assert (pos[:, 1] == pos[:, 1].max()).sum() == 99 and (pos[:, 1] == pos[:, 1].min()).sum() == 99
+    assert m.particle_names[0] == "G0_0_0" and m.particle_names[-1] == "G8_3_10"
+    assert all(re.search(r"[G]\d+[_]\d+[_]\d+$", m.geom_name(4 + k)) for k in range(270))  # ultrasound.py:724
+    assert not re.search(r"[G]\d+[_]\d+[_]\d+$", m.geom_name(3))
+    np.testing.assert_allclose(np.linalg.norm(m.part_axis, axis=1), 1)
+    # torso body rotation maps the thin local axis (y) to world z: world half extents (0.175, 0.14, 0.0525)
+    from rui_b200.model import quat2mat
+    R = quat2mat(m.params.torso_quat)
+    np.testing.assert_allclose(np.abs(pos @ R.T).max(axis=0), [0.175, 0.14, 0.0525], atol=1e-12)
+    # every particle has 2..5 neighbours, table is symmetric
+    nb = m.part_nbr
+    deg = (nb >= 0).sum(axis=1)
+    assert deg.min() >= 3 and deg.max() <= 4 and deg.sum() == 2 * 536
+    for i in range(270):
+        for j in nb[i][nb[i] >= 0]:
+            assert i in nb[j]
+    assert abs(m.g_body_mass[m.ids[6]:].sum() - 2.7) < 1e-12
+
+
+def test_rigid_model_and_arm_tables(rigid_model):
+    m = rigid_model.model
+    assert (m.nq, m.nv) == (7, 7)
+    L = m.arm_link
+    assert abs(L[6, 15] - (0.5 + 0.5 + 1.0)) < 1e-12  # link 7 + hand + probe welded
+    assert abs(L[:, 15].sum() - (3 + 3 + 2 + 2 + 2 + 1.5 + 2.0)) < 1e-12
+    assert m.dof_invweight0.shape == (7,) and np.all(m.dof_invweight0 > 0)
+
+
+def test_shard_range_partitions_the_env_ids():
+    from rui_b200.dist import shard_range
+    for total, world in ((65536, 8), (65536, 2), (4096, 1), (10, 4), (7, 8)):
+        seen = []
+        for r in range(world):
+            off, n = shard_range(total, r, world)
+            seen += list(range(off, off + n))
+        assert seen == list(range(total))
+    with pytest.raises(ValueError):
+        shard_range(8, 3, 2)

@@ -1,0 +1,166 @@
+"""Known-answer tests of the float64 oracle (the parity reference for the CUDA path).
+
+The reference ships no tests and its physics lives in a closed binary, so the oracle is
+pinned here by physics that has a closed-form answer and by an independent numpy formulation of the inertia."""
+import numpy as np
+import pytest
+
+from conftest import CC_FIXED, CC_TRACK
+from rui_b200 import abi
+from rui_b200.model import build_model, forward_kinematics, mass_matrix
+
+
+def _cfg(cc, **kw):
+    return abi.make_config(1, cc, control_freq=500, horizon=1000, **kw)
+
+
+def test_philox_known_answers(O):
+    # Random123 known-answer vectors for Philox4x32-10
+    assert [hex(x) for x in O.philox(0, 0, 0, 0, 0)] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert [hex(x) for x in O.philox(0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF)] == [
+        "0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(x) for x in O.philox(0x299F31D0A4093822, 0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344)] == [
+        "0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_inertia_matches_numpy_formulation(O, soft_model):
+    e = O.OracleEnv(soft_model, _cfg(CC_TRACK, seed=5, initial_probe_pos_randomization=True), 0)
+    e.reset()
+    q = e.get_state()[0]
+    rng = np.random.default_rng(0)
+    q[14:] += rng.normal(scale=2e-3, size=270)
+    e.set_state(qpos=q)
+    e.forward()
+    M_np, _, _ = mass_matrix(soft_model.model, e.get_state()[0])
+    M = e.M
+    assert np.abs(M - M.T).max() < 1e-12
+    assert np.abs(M - M_np).max() < 1e-12
+    assert np.linalg.eigvalsh(M).min() > 0
+    # arrow structure the CUDA kernel relies on: sliders couple only with the free translation and themselves
+    S = M[13:, 13:]
+    assert np.abs(S - np.diag(np.diag(S))).max() < 1e-14
+    assert np.abs(M[10:13, 13:]).max() < 1e-12 and np.abs(M[:7, 7:]).max() == 0
+
+
+def test_bias_is_gravity_torque_at_rest(O, rigid_model):
+    """qfrc_bias at zero velocity = -d(potential)/dq, checked by finite differences of the potential energy."""
+    m = rigid_model.model
+    e = O.OracleEnv(rigid_model, _cfg(CC_FIXED), 0)
+    q0 = np.array(m.params.init_qpos) + 0.1
+    e.set_state(qpos=q0, qvel=np.zeros(7))
+    e.forward()
+    bias = e.bias
+
+    def pot(q):
+        xpos, xmat = forward_kinematics(m, q)
+        return sum(m.g_body_mass[b] * 9.81 * (xpos[b] + xmat[b] @ m.g_body_ipos[b])[2] for b in range(1, m.nbody))
+
+    for j in range(7):
+        dq = np.zeros(7); dq[j] = 1e-6
+        assert abs((pot(q0 + dq) - pot(q0 - dq)) / 2e-6 - bias[j]) < 1e-6
+
+
+def test_free_arm_energy_is_conserved_without_damping(O):
+    """No damping, no torque, no contact: semi-implicit Euler keeps total energy within O(h) over 200 steps."""
+    from rui_b200.model import SceneParams
+    pk = abi.PackedModel(build_model(SceneParams(soft_torso=False, joint_damping=0.0)))
+    m = pk.model
+    cc = dict(CC_FIXED, impedance_mode="wrench")  # wrench mode with a zero action = zero task-space force
+    e = O.OracleEnv(pk, _cfg(cc), 0)
+    e.reset()
+    q0 = np.array([0.3, -0.4, 0.2, -1.6, 0.1, 1.2, 0.5])
+    ts = e.get_state()[3]
+    ts[abi.TS_INIT_JOINT:abi.TS_INIT_JOINT + 7] = q0
+    e.set_state(qpos=q0, qvel=np.zeros(7), task=ts)
+
+    def energy():
+        q, v = e.get_state()[:2]
+        M, xpos, xmat = mass_matrix(m, q)
+        pe = sum(m.g_body_mass[b] * 9.81 * (xpos[b] + xmat[b] @ m.g_body_ipos[b])[2] for b in range(1, m.nbody))
+        return 0.5 * v @ M @ v + pe
+
+    # the wrench-mode torque is bias compensation + null-space PD: remove both by stepping the raw dynamics
+    E0 = energy()
+    for _ in range(100):
+        e.forward(np.zeros(7))
+        assert e.nefc == 0  # no contact, no joint limit: pure rigid-body dynamics
+        q, v = e.get_state()[:2]
+        a = e.qacc
+        v = v + 0.002 * a
+        e.set_state(qpos=q + 0.002 * v, qvel=v)
+    E1 = energy()
+    q, v = e.get_state()[:2]
+    assert np.abs(v).max() > 0.3  # it really fell
+    assert abs(E1 - E0) < 0.02 * abs(0.5 * v @ mass_matrix(m, q)[0] @ v)
+
+
+def test_ik_reaches_target(O, soft_model):
+    e = O.OracleEnv(soft_model, _cfg(CC_TRACK), 0)
+    for target in ([0.05, 0.02, 0.9], [-0.1, -0.08, 0.88], [0.14, 0.09, 0.91]):
+        q = e.ik(target)
+        st = e.get_state()
+        st[0][:7] = q
+        e.set_state(qpos=st[0])
+        e.forward()
+        _, pos, mat = e.eef()
+        assert np.abs(pos - target).max() < 1e-8
+        quat = O.mat2quat_xyzw(mat.reshape(9))
+        g = np.array(abi.GOAL_QUAT_XYZW)
+        assert min(np.abs(quat - g).max(), np.abs(quat + g).max()) < 1e-6
+        lo, hi = soft_model.model.g_jnt_range[:, 0], soft_model.model.g_jnt_range[:, 1]
+        assert np.all(q > lo) and np.all(q < hi)
+
+
+def test_torso_settles_with_contact_force_equal_weight(O, soft_model):
+    """Probe far away: after settling, the table normal forces carry the torso's weight."""
+    m = soft_model.model
+    e = O.OracleEnv(soft_model, _cfg(CC_FIXED), 0)
+    e.reset()
+    q, v, w, ts = e.get_state()
+    q[:7] = m.params.init_qpos
+    ts[abi.TS_INIT_JOINT:abi.TS_INIT_JOINT + 7] = q[:7]
+    e.set_state(qpos=q, qvel=v, task=ts)
+    for _ in range(150):
+        e.step(np.zeros(6))
+    c = e.contacts()
+    assert set(c["geom2"]) == {1} and c["geom1"].min() >= 4  # only particle-table contacts
+    # force on geom2 (table) along the contact normal (0,0,-1): weight pushes the table down
+    fz_on_table = sum(f[0] * fr[0][2] + f[1] * fr[1][2] + f[2] * fr[2][2] for f, fr in zip(c["force"], c["frame"]))
+    weight = (270 * 0.01 + 0.01) * 9.81
+    assert abs(-fz_on_table - weight) < 0.03 * weight
+    v = e.get_state()[1]
+    assert np.abs(v[7:13]).max() < 5e-3
+
+
+def test_single_soft_contact_closed_form(O):
+    """Probe tip pressed into the rigid table at rest, arm locked by a huge gain: compare the contact force of the
+    7-DoF solve with the closed-form 1-row answer f = -D (J a - aref) of the regularised constraint."""
+    from rui_b200.model import SceneParams
+    pk = abi.PackedModel(build_model(SceneParams(soft_torso=False, table_friction=1e-6, probe_friction=1e-6)))  # frictionless
+    m = pk.model
+    e = O.OracleEnv(pk, _cfg(CC_FIXED), 0)
+    e.reset()
+    # find a configuration with the probe tip 1 mm inside the table
+    e2 = O.OracleEnv(abi.PackedModel(build_model()), _cfg(CC_TRACK), 0)
+    q = e2.ik([0.0, 0.0, 0.8 - 0.001])
+    e.set_state(qpos=q, qvel=np.zeros(7))
+    e.forward(np.zeros(7))
+    c = e.contacts()
+    assert len(c["dist"]) == 1 and abs(c["dist"][0] + 0.001) < 2e-5  # the goal orientation is a hair off vertical
+    depth = -c["dist"][0]
+    J, pos, _ = e.eef()
+    # contact row: normal (0,0,1), point = contact pos; contact point Jacobian from the site Jacobian
+    r = c["pos"][0] - pos
+    Jn = J[2] + np.cross(J[3:].T, r)[:, 2]
+    M, a0 = e.M, e.qacc_smooth
+    dmin, dmax, width = 0.9, 0.95, 0.001
+    assert depth / width >= 1
+    imp = dmax  # |r| >= width
+    tc = 0.02
+    K, B = 1 / (dmax ** 2 * tc ** 2), 2 / (dmax * tc)
+    aref = -K * imp * (-depth)
+    R = (1 - imp) / imp * m.body_invweight0[m.ids[4], 0]
+    A = Jn @ np.linalg.solve(M, Jn)
+    f = (aref - Jn @ a0) / (A + R)  # frictionless 1-row solution; friction rows carry ~0 at rest
+    assert f > 0
+    assert abs(c["force"][0][0] - f) < 2e-3 * f

@@ -1,0 +1,109 @@
+"""Oracle task layer vs the golden vectors produced by executing the reference's own Python
+(tests/golden/make_golden.py): utils/quaternion.py, Ultrasound.reward/_post_action/_check_terminated/
+get_trajectory.  float64, tolerance = round-off only."""
+import numpy as np
+import pytest
+
+from rui_b200 import abi
+from rui_b200.env import probe_torso_contact
+
+
+def test_quaternion(golden, O):
+    for c in golden["quaternion"]:
+        q1, q2 = np.array(c["q1"]), np.array(c["q2"])
+        np.testing.assert_allclose(O.difference_quat(q1, q2), c["difference"], atol=1e-14)
+        d = O.distance_quat(q1, q2)
+        if c["distance"] is None:  # the reference raises (quaternion.py:51) when q1*conj(q2) == (-1,0,0,0): treated as 0
+            assert d == 0.0
+        else:
+            assert abs(d - c["distance"]) < 1e-12
+
+
+def test_reward(golden, O):
+    assert len(golden["reward"]) >= 50
+    for c in golden["reward"]:
+        r, pe, oe = O.reward(c["eef_pos"], c["eef_quat_xyzw"], c["traj_pt"], c["vel_mean"], c["fz_mean"], c["dfz"], c["in_contact"])
+        assert abs(r - c["reward"]) < 1e-12
+        np.testing.assert_allclose(pe, c["pos_error"], rtol=1e-12, atol=1e-15)
+        assert abs(oe - c["ori_error"]) < 1e-12
+        assert 0.0 <= r <= 12.0
+
+
+def test_post_action_sequences(golden, O):
+    jr = np.zeros(14)  # joint limits unused here: check_q_limits is stubbed to False in the golden generator
+    for seq in golden["post_action"]:
+        ts = np.zeros(abi.TASK_DIM)
+        ts[abi.TS_TRAJ_START:abi.TS_TRAJ_START + 3] = seq["start"]
+        ts[abi.TS_TRAJ_END:abi.TS_TRAJ_END + 3] = seq["end"]
+        ts[abi.TS_U0] = seq["u0"]
+        u = min(max(seq["u0"], 0.0), 1.0)
+        ts[abi.TS_TRAJ_PT:abi.TS_TRAJ_PT + 3] = np.array(seq["start"]) + u * (np.array(seq["end"]) - np.array(seq["start"]))
+        ts[abi.TS_FZ_MEAN] = seq["fz_mean0"]
+        n_done = 0
+        for t, s in enumerate(seq["steps"]):
+            ts[abi.TS_TIMESTEP] = t + 1
+            r, d = O.post_action(ts, seq["horizon"], seq["control_freq"], seq["early_termination"], jr, s["eef_pos"], s["eef_quat_xyzw"],
+                                 s["hand_vel"], s["fz"], s["in_contact"], None)
+            assert abs(r - s["reward"]) < 1e-11, (t, r, s["reward"])
+            assert d == s["done"], t
+            np.testing.assert_allclose(ts[abi.TS_TRAJ_PT:abi.TS_TRAJ_PT + 3], s["traj_pt"], atol=1e-14)
+            np.testing.assert_allclose(ts[abi.TS_TRAJ_PT:abi.TS_TRAJ_PT + 3], s["controller_traj_pos"], atol=1e-14)
+            assert abs(ts[abi.TS_VEL_MEAN] - s["vel_mean"]) < 1e-13
+            assert abs(ts[abi.TS_DFZ] - s["dfz"]) < 1e-9
+            assert abs(ts[abi.TS_FZ_MEAN] - s["fz_mean"]) < 1e-12
+            assert bool(ts[abi.TS_TOUCHED]) == s["touched"]
+            n_done += d
+        assert n_done <= 1
+    # the four sequences exercise: orientation termination, horizon, lost contact, trajectory deviation
+    assert [s["steps"][-1]["done"] for s in golden["post_action"]] == [True, True, True, True]
+
+
+def test_contact_query(golden):
+    for c in golden["contact_query"]:
+        assert probe_torso_contact(c["names"]) == c["in_contact"]
+
+
+def test_trajectory_grid(golden, O):
+    g = golden["trajectory"]
+    t = g["torso_xpos"]
+    gx = [O.grid_point(t, i, 0)[0] for i in range(50)]
+    gy = [O.grid_point(t, 0, i)[1] for i in range(50)]
+    np.testing.assert_allclose(gx, g["grid_x"], atol=1e-15)
+    np.testing.assert_allclose(gy, g["grid_y"], atol=1e-15)
+    for d in g["draws_seed3"]:  # every reference draw is a grid point at z = torso z + 0.039
+        for p in (d["start"], d["end"]):
+            assert min(abs(np.array(g["grid_x"]) - p[0])) < 1e-15 and min(abs(np.array(g["grid_y"]) - p[1])) < 1e-15
+            assert abs(p[2] - O.grid_point(t, 0, 0)[2]) < 1e-15
+    assert g["deterministic"]["start"] == [0.062, -0.020, 0.896] and g["deterministic"]["end"] == [-0.032, -0.075, 0.896]
+
+
+def test_constants(golden):
+    c = golden["constants"]
+    np.testing.assert_allclose(c["goal_quat"], abi.GOAL_QUAT_XYZW, atol=0)
+    assert (c["pos_error_mul"], c["ori_error_mul"], c["vel_error_mul"], c["force_error_mul"], c["der_force_error_mul"]) == (90, 0.2, 45, 0.7, 0.01)
+    assert (c["pos_reward_mul"], c["ori_reward_mul"], c["vel_reward_mul"], c["force_reward_mul"], c["der_force_reward_mul"]) == (5, 1, 1, 3, 2)
+    assert (c["goal_velocity"], c["goal_contact_z_force"], c["alpha"], c["pos_error_threshold"], c["ori_error_threshold"]) == (0.04, 5, 0.1, 1.0, 0.10)
+    assert (c["top_torso_offset"], c["x_range"], c["y_range"], c["grid_pts"], c["sigma"]) == (0.039, 0.15, 0.09, 50, 0.010)
+
+
+def test_reset_noise_and_draws(golden, O, soft_model):
+    """Seeded Philox reset: integer draws in range, probe noise matches the reference's sigmas (ultrasound.py:880-881)."""
+    from conftest import CC_TRACK
+    g = golden["trajectory"]
+    cfg = abi.make_config(1, CC_TRACK, control_freq=500, torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=11,
+                          reset_eef_bias=(0, 0, 0))
+    dev, ks, bs = [], [], []
+    for gid in range(160):
+        e = O.OracleEnv(soft_model, cfg, gid)
+        obs = e.reset()
+        ts = e.get_state()[3]
+        ks.append(ts[abi.TS_STIFFNESS]); bs.append(ts[abi.TS_DAMPING])
+        assert 1300 <= ts[abi.TS_STIFFNESS] < 1600 and ts[abi.TS_STIFFNESS] == int(ts[abi.TS_STIFFNESS])
+        assert 17 <= ts[abi.TS_DAMPING] < 41 and ts[abi.TS_DAMPING] == int(ts[abi.TS_DAMPING])
+        assert 0 <= ts[abi.TS_U0] < 1
+        for k in (abi.TS_TRAJ_START, abi.TS_TRAJ_END):
+            assert min(abs(np.array(g["grid_x"]) - ts[k])) < 1e-12 and min(abs(np.array(g["grid_y"]) - ts[k + 1])) < 1e-12
+        dev.append(obs[12:15])  # eef - traj_pt = noise (IK converged, zero bias)
+    std = np.std(dev, axis=0)
+    np.testing.assert_allclose(std, g["noise_std"], rtol=0.25)
+    assert len(set(ks)) > 50 and len(set(bs)) > 15
