@@ -37,7 +37,7 @@ extern "C" {
 #define USIM_TASK_DIM 48     /* per-env task-state record, layout below */
 #define USIM_MAX_ACTION 7
 #define USIM_NV_ARM 7
-#define USIM_MAX_CONTACTS 160 /* per env (reference: nconmax 5000 for the whole scene) */
+#define USIM_MAX_CONTACTS 128 /* per env (reference: nconmax 5000 for the whole scene) */
 
 /* impedance modes of the OSC_POSE controller (rl_config.yaml:41, main.py:33) */
 enum { USIM_MODE_FIXED = 0, USIM_MODE_TRACKING = 1, USIM_MODE_VARIABLE_Z = 2, USIM_MODE_WRENCH = 3 };
@@ -113,7 +113,7 @@ typedef struct usim_config {
   int32_t deterministic_trajectory;
   int32_t uncouple_pos_ori;
   int32_t solver_iterations; /* CG iteration cap per step (device) */
-  int32_t reserved0;
+  int32_t precond_rebuilds;   /* preconditioner rebuilds allowed per solve when contact zones change (0: default 8) */
   uint64_t seed;
   double control_freq;
   double kp[6], damping_ratio[6];      /* fixed mode (rl_config.yaml:39-40) */

@@ -11,7 +11,7 @@ import os
 from .abi import UsimConfig, UsimModel
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libusim.so")
+LIB_PATH = os.environ.get("USIM_LIB") or os.path.join(_HERE, "libusim.so")  # USIM_LIB: developer override (kernel variants)
 
 _vp = C.c_void_p
 _lib = None

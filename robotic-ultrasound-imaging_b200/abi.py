@@ -15,7 +15,7 @@ from .model import UltrasoundModel
 USIM_ABI_VERSION = 1
 OBS_DIM = 19
 TASK_DIM = 48
-MAX_CONTACTS = 160
+MAX_CONTACTS = 128
 DIAG_DIM = 24
 
 GOAL_QUAT_XYZW = (-0.69192486, 0.72186726, -0.00514253, -0.01100909)  # ultrasound.py:174
@@ -59,7 +59,7 @@ class UsimConfig(C.Structure):
         ("abi_version", C.c_int32), ("num_envs", C.c_int32), ("env_id_offset", C.c_int32), ("impedance_mode", C.c_int32),
         ("horizon", C.c_int32), ("early_termination", C.c_int32), ("solref_randomization", C.c_int32),
         ("probe_pos_randomization", C.c_int32), ("deterministic_trajectory", C.c_int32), ("uncouple_pos_ori", C.c_int32),
-        ("solver_iterations", C.c_int32), ("reserved0", C.c_int32),
+        ("solver_iterations", C.c_int32), ("precond_rebuilds", C.c_int32),
         ("seed", C.c_uint64),
         ("control_freq", C.c_double),
         ("kp", C.c_double * 6), ("damping_ratio", C.c_double * 6),
@@ -138,7 +138,7 @@ def make_config(
     seed: int = 0,
     env_id_offset: int = 0,
     solver_iterations: int = 40,
-    solver_tolerance: float = 1e-6,
+    solver_tolerance: float = 3e-6,
     reset_eef_bias=ART_RESET_EEF_BIAS,
 ) -> UsimConfig:
     """Translate the ``suite.make("Ultrasound", ...)`` kwargs (rl_config.yaml:18-57,

@@ -24,13 +24,13 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = LIB, extra=()) -> str:
+    if not force and out == LIB and not needs_build():
         return LIB
     cmd = [
         NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
         "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if verbose else "-O3",
-        "-o", LIB, os.path.join(CSRC, "usim.cu"),
+        "-o", out, os.path.join(CSRC, "usim.cu"), *extra,
     ]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
@@ -38,7 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libusim.so")
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

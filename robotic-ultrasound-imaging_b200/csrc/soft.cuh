@@ -14,15 +14,18 @@
 #pragma once
 #include "common.cuh"
 
-#define WARPS_PER_CTA 4
+#ifndef WARPS_PER_CTA
+#define WARPS_PER_CTA 1 // one env per CTA: no CTA waits for its slowest env (measured 1/2/4/8 warps: 2.17/2.12/1.96/1.82 M steps/s)
+#endif
 #define NPAIR_MAX 544
 
 struct __align__(16) WS {
-  float qs[NPART_MAX], vs[NPART_MAX];                  // slider position / velocity
-  float x[QPAD], Hx[QPAD], rhs[QPAD], grad[QPAD], pg[QPAD], s[QPAD], hs[QPAD];
-  float dg[NPART_MAX], kx[NPART_MAX], ky[NPART_MAX], kz[NPART_MAX], df[NPART_MAX];
+  float qs[NPART_MAX];                                 // slider position (slider velocity lives in hs[13..] until the CG loop starts)
+  // Hx holds (M+E)x - rhs; during set-up `grad` accumulates rhs (= qfrc_smooth + J_eq^T D aref)
+  float x[QPAD], Hx[QPAD], grad[QPAD], pg[QPAD], s[QPAD], hs[QPAD];
+  float dg[NPART_MAX], dg0[NPART_MAX], kx[NPART_MAX], ky[NPART_MAX], kz[NPART_MAX], df[NPART_MAX]; // dg0: diagonal without contacts
   float Dp[NPAIR_MAX];                                 // D of each "smooth" pair
-  float cpos[3][DEV_MAXC], cn[3][DEV_MAXC], caref[3][DEV_MAXC], cjar[3][DEV_MAXC], cjv[3][DEV_MAXC];
+  float cpos[3][DEV_MAXC], cn[3][DEV_MAXC], cjar[3][DEV_MAXC], cjv[3][DEV_MAXC]; // cjv holds aref until the first J*x
   float cD[DEV_MAXC], cdist[DEV_MAXC];
   short cpart[DEV_MAXC];
   unsigned char ctype[DEV_MAXC], czone[DEV_MAXC];
@@ -116,10 +119,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
   // ------------------------------------------------------------------ load
   for (int i = lane; i < ARMBUF; i += 32) w.ab[i] = armbuf[(size_t)env * ARMBUF + i];
   for (int i = lane; i < USIM_TASK_DIM; i += 32) w.ts[i] = ts_g[i];
-  for (int i = lane; i < QPAD; i += 32) { w.x[i] = i < nv ? wm_g[i] : 0.f; w.rhs[i] = 0.f; }
+  for (int i = lane; i < QPAD; i += 32) { w.x[i] = i < nv ? wm_g[i] : 0.f; w.grad[i] = 0.f; }
   for (int i = lane; i < np; i += 32) {
-    w.qs[i] = qp_g[14 + i]; w.vs[i] = qv_g[13 + i];
-    w.kx[i] = 0.f; w.ky[i] = 0.f; w.kz[i] = 0.f;
+    w.qs[i] = qp_g[14 + i]; w.hs[13 + i] = qv_g[13 + i];
   }
   if (lane < 7) w.qdarm[lane] = qv_g[lane];
   float quat[4] = {1, 0, 0, 0};
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     const float m = dm.part_mass;
     for (int i = lane; i < np; i += 32) {
       v3 ah = ld3(pt.axis + 3 * i), r0 = ld3(pt.pos + 3 * i);
-      float q = w.qs[i], sd = w.vs[i];
+      float q = w.qs[i], sd = w.hs[13 + i];
       v3 c = r0 + (q - off) * ah;
       a_mc[0] += m * c.x; a_mc[1] += m * c.y; a_mc[2] += m * c.z;
       float cc = dot(c, c);
@@ -161,14 +163,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       v3 T = cross(c, F);
       a_F[0] += F.x; a_F[1] += F.y; a_F[2] += F.z; a_T[0] += T.x; a_T[1] += T.y; a_T[2] += T.z;
       a_q += q; a_v += sd;
-      w.rhs[13 + i] = -dot(ah, F);
+      w.grad[13 + i] = -dot(ah, F);
       // "fix" equality of this slider
       float K, B, imp;
       kbi(dm.solref[0], dm.solref[1], q, &K, &B, &imp);
       float D = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * pt.iw_dof[i]);
       w.df[i] = D;
       w.dg[i] = m + D;
-      w.rhs[13 + i] += D * (-B * sd - K * imp * q);
+      w.grad[13 + i] += D * (-B * sd - K * imp * q);
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) { a_mc[k] = wsum(a_mc[k]); a_F[k] = wsum(a_F[k]); a_T[k] = wsum(a_T[k]); }
@@ -202,26 +204,26 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       v3 bv = mv(R, sF) - dm.center_mass * ld3(dm.g);
       v3 Iw = symv(dm.rot_I, wl);
       v3 bw = sT + cross(wl, Iw);
-      w.rhs[7] = -bv.x - dm.free_damp * vlin.x; w.rhs[8] = -bv.y - dm.free_damp * vlin.y; w.rhs[9] = -bv.z - dm.free_damp * vlin.z;
-      w.rhs[10] = -bw.x - dm.free_damp * wl.x; w.rhs[11] = -bw.y - dm.free_damp * wl.y; w.rhs[12] = -bw.z - dm.free_damp * wl.z;
+      w.grad[7] = -bv.x - dm.free_damp * vlin.x; w.grad[8] = -bv.y - dm.free_damp * vlin.y; w.grad[9] = -bv.z - dm.free_damp * vlin.z;
+      w.grad[10] = -bw.x - dm.free_damp * wl.x; w.grad[11] = -bw.y - dm.free_damp * wl.y; w.grad[12] = -bw.z - dm.free_damp * wl.z;
     }
     __syncwarp();
     // "smooth" pair equalities (carry solrefsmooth = (-stiffness, -damping) of this episode)
     for (int pr = lane; pr < dm.npair; pr += 32) {
       int a = eq_pairs[2 * pr], b = eq_pairs[2 * pr + 1];
-      float pos = w.qs[a] - w.qs[b], vel = w.vs[a] - w.vs[b], K2, B2, imp2;
+      float pos = w.qs[a] - w.qs[b], vel = w.hs[13 + a] - w.hs[13 + b], K2, B2, imp2;
       kbi(ksm, bsm, pos, &K2, &B2, &imp2);
       float D = 1.f / fmaxf(1e-15f, (1.f - imp2) / imp2 * (pt.iw_dof[a] + pt.iw_dof[b]));
       w.Dp[pr] = D;
       float ar = D * (-B2 * vel - K2 * imp2 * pos);
-      atomicAdd(&w.rhs[13 + a], ar); atomicAdd(&w.rhs[13 + b], -ar);
+      atomicAdd(&w.grad[13 + a], ar); atomicAdd(&w.grad[13 + b], -ar);
       atomicAdd(&w.dg[a], D); atomicAdd(&w.dg[b], D);
     }
     __syncwarp();
-    for (int i = lane; i < np; i += 32) { w.rhs[13 + i] += w.Dt * w.areft; w.dg[i] += w.Dt; }
+    for (int i = lane; i < np; i += 32) { w.grad[13 + i] += w.Dt * w.areft; w.dg0[i] = w.dg[i] + w.Dt; }
   }
   if (lane < 7) {
-    w.rhs[lane] = w.ab[AB_QS + lane];
+    w.grad[lane] = w.ab[AB_QS + lane];
     // joint limits (margin 0)
     float q = qp_g[lane], lo = dm.jnt_lo[lane], hi = dm.jnt_hi[lane], dist = 0.f, sg = 0.f;
     if (q - lo < 0.f) { dist = q - lo; sg = 1.f; } else if (hi - q < 0.f) { dist = hi - q; sg = -1.f; }
@@ -297,6 +299,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       }
     }
   }
+  const int ncon_found = ncon;
   if (ncon > DEV_MAXC) ncon = DEV_MAXC;
   __syncwarp();
 
@@ -321,16 +324,16 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     float diagA = 0.f;
     if (type != 2) {
       v3 aw = mv(R, ld3(pt.axis + 3 * i));
-      rel = rel - (vlin + cross(ww, pos - P) + w.vs[i] * aw);
+      rel = rel - (vlin + cross(ww, pos - P) + w.hs[13 + i] * aw);
       diagA += pt.iw_body[i];
     }
     if (type != 0) { rel = rel + Vs + cross(Ws, pos - site); diagA += dm.iw_probe; }
     float K, B, imp;
     kbi(dm.solref[0], dm.solref[1], w.cdist[c], &K, &B, &imp);
     w.cD[c] = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * diagA);
-    w.caref[0][c] = -B * dot(nn, rel) - K * imp * w.cdist[c];
-    w.caref[1][c] = -B * dot(t1, rel);
-    w.caref[2][c] = -B * dot(t2, rel);
+    w.cjv[0][c] = -B * dot(nn, rel) - K * imp * w.cdist[c];
+    w.cjv[1][c] = -B * dot(t1, rel);
+    w.cjv[2][c] = -B * dot(t2, rel);
   }
   __syncwarp();
 
@@ -401,21 +404,23 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       if (type != 2) rel = rel - (iv + cross(iw, pos - P) + in[13 + i] * mv(R, ld3(pt.axis + 3 * i)));
       if (type != 0) rel = rel + V + cross(W, pos - site);
       float o0 = dot(nn, rel), o1 = dot(t1, rel), o2 = dot(t2, rel);
-      if (sub_aref) { o0 -= w.caref[0][c]; o1 -= w.caref[1][c]; o2 -= w.caref[2][c]; }
+      if (sub_aref) { o0 -= w.cjv[0][c]; o1 -= w.cjv[1][c]; o2 -= w.cjv[2][c]; }
       out[0][c] = o0; out[1][c] = o1; out[2][c] = o2;
     }
     __syncwarp();
   };
   // grad = Hx - rhs - J^T f(jar); also returns probe wrench (force, torque about the site) via w.red[12..17]
-  auto update_grad = [&]() {
-    for (int i = lane; i < QPAD; i += 32) w.grad[i] = i < nv ? w.Hx[i] - w.rhs[i] : 0.f;
+  auto update_grad = [&]() -> bool {
+    for (int i = lane; i < QPAD; i += 32) w.grad[i] = i < nv ? w.Hx[i] : 0.f;
     __syncwarp();
+    bool changed = false;
     float g[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // particle-side (force, torque about P), probe-side (force, torque about site)
     for (int c = lane; c < ncon; c += 32) {
       int type = w.ctype[c], i = w.cpart[c], zone;
       float fr, mu, f0, f1, f2, Dn = w.cD[c];
       contact_params(type, fr, mu);
       cone_force(w.cjar[0][c], w.cjar[1][c], w.cjar[2][c], Dn, Dn * dm.impratio, mu, fr, f0, f1, f2, zone);
+      changed |= (zone != (int)w.czone[c]);
       w.czone[c] = (unsigned char)zone;
       if (zone == 0) continue;
       v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), t1, t2;
@@ -455,6 +460,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       for (int k = 0; k < 6; k++) w.red[12 + k] = g[6 + k];
     }
     __syncwarp();
+    return __any_sync(0xffffffffu, changed);
   };
   // pg = P^-1 grad  (arm: dense 7x7 Cholesky; torso: arrow with the 6x6 Schur complement Sf)
   auto precond = [&]() {
@@ -503,27 +509,63 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
 
   // ------------------------------------------------------------------ K6: initial point = warm start
   applyH(w.x, w.Hx);
+  const float rhsn = sqrtf(vdot(w.grad, w.grad));
+  for (int i = lane; i < nv; i += 32) w.Hx[i] -= w.grad[i];
+  for (int c = lane; c < ncon; c += 32) w.czone[c] = 255; // "unknown": the first update always reports a change
+  __syncwarp();
   dense_vel(w.x);
   contactJ(w.x, w.cjar, true);
   update_grad();
 
-  // preconditioner from the initial active set
-  {
+  // preconditioner from the current active set (contact zones); rebuilt when the zones change
+  auto build_precond = [&]() {
+    for (int i = lane; i < np; i += 32) { w.dg[i] = w.dg0[i]; w.kx[i] = 0.f; w.ky[i] = 0.f; w.kz[i] = 0.f; }
+    __syncwarp();
     float kf[21], kp[21];
 #pragma unroll
     for (int k = 0; k < 21; k++) { kf[k] = 0.f; kp[k] = 0.f; }
     for (int c = lane; c < ncon; c += 32) {
       int zone = w.czone[c], type = w.ctype[c], i = w.cpart[c];
       if (zone == 0) continue;
-      float Dn = w.cD[c], Dtg = zone == 2 ? Dn * dm.impratio : 0.f;
+      float Dn = w.cD[c];
       v3 nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]);
-      // K = Dt I + (Dn - Dt) n n^T
+      // world-frame 3x3 contact Hessian K = F^T H F (F = contact frame rows, H = Hessian of the cone cost wrt jar)
       float Km[9];
       float nv3[3] = {nn.x, nn.y, nn.z};
+      if (zone == 2) { // bottom zone: H = diag(Dn, Dt, Dt)  ->  K = Dt I + (Dn - Dt) n n^T
+        float Dtg = Dn * dm.impratio;
 #pragma unroll
-      for (int a = 0; a < 3; a++)
+        for (int a = 0; a < 3; a++)
 #pragma unroll
-        for (int b = 0; b < 3; b++) Km[3 * a + b] = (a == b ? Dtg : 0.f) + (Dn - Dtg) * nv3[a] * nv3[b];
+          for (int b = 0; b < 3; b++) Km[3 * a + b] = (a == b ? Dtg : 0.f) + (Dn - Dtg) * nv3[a] * nv3[b];
+      } else { // middle zone: exact Hessian of 0.5 Dm (N - mu T)^2
+        float fr, mu;
+        contact_params(type, fr, mu);
+        v3 t1, t2;
+        make_frame(nn, &t1, &t2);
+        float N = w.cjar[0][c] * mu, U1 = w.cjar[1][c] * fr, U2 = w.cjar[2][c] * fr, T = fmaxf(sqrtf(U1 * U1 + U2 * U2), 1e-20f);
+        float Dm = Dn / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T, u1 = U1 / T, u2 = U2 / T;
+        float g3[3] = {1.f, -mu * u1, -mu * u2}, sc[3] = {mu, fr, fr}, kk = -Dm * mu * NmT / T;
+        float H3[9];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) H3[3 * a + b] = Dm * g3[a] * g3[b];
+        H3[4] += kk * (1.f - u1 * u1); H3[5] -= kk * u1 * u2; H3[7] -= kk * u1 * u2; H3[8] += kk * (1.f - u2 * u2);
+        float Fm[9] = {nn.x, nn.y, nn.z, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z};
+#pragma unroll
+        for (int a = 0; a < 9; a++) Km[a] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) {
+            float hab = sc[a] * H3[3 * a + b] * sc[b];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+              for (int q = 0; q < 3; q++) Km[3 * r + q] += hab * Fm[3 * a + r] * Fm[3 * b + q];
+          }
+      }
       for (int side = 0; side < 2; side++) {
         if (side == 0 && type == 2) continue;
         if (side == 1 && type == 0) continue;
@@ -639,13 +681,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     __syncwarp();
     if (lane == 0) chol<7>(w.Pa);
     __syncwarp();
-  }
+  };
+  build_precond();
+  int rebuilds = 0;
 
   precond();
   for (int i = lane; i < QPAD; i += 32) w.s[i] = i < nv ? -w.pg[i] : 0.f;
   __syncwarp();
   float gpg = vdot(w.grad, w.pg);
-  const float rhsn = sqrtf(vdot(w.rhs, w.rhs));
   float gnorm = sqrtf(vdot(w.grad, w.grad));
   int iters = 0;
   const int maxit = mode == 1 ? 2 * dm.iters : dm.iters;
@@ -658,7 +701,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     contactJ(w.s, w.cjv, false);
     // ---- exact line search: Newton on phi'(alpha)
     float q1 = 0.f, q2 = 0.f;
-    for (int i = lane; i < nv; i += 32) { q1 += w.s[i] * (w.Hx[i] - w.rhs[i]); q2 += w.s[i] * w.hs[i]; }
+    for (int i = lane; i < nv; i += 32) { q1 += w.s[i] * w.Hx[i]; q2 += w.s[i] * w.hs[i]; }
     q1 = wsum(q1); q2 = wsum(q2);
     float alpha = 0.f, lo = 0.f, hi = -1.f, d0abs = 0.f;
     for (int ls = 0; ls < 8; ls++) {
@@ -690,12 +733,15 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       w.cjar[0][c] += alpha * w.cjv[0][c]; w.cjar[1][c] += alpha * w.cjv[1][c]; w.cjar[2][c] += alpha * w.cjv[2][c];
     }
     __syncwarp();
-    update_grad();
+    bool changed = update_grad();
     float gpo = vdot(w.grad, w.pg); // with the previous pg (Polak-Ribiere)
+    bool restart = false;
+    // soft scene: rebuild when the active set moved; rigid scene (7 unknowns): exact Hessian every iteration = Newton
+    if ((changed && rebuilds < dm.max_rebuilds) || (!dm.soft && ncon > 0)) { build_precond(); rebuilds++; restart = true; }
     precond();
     float gpn = vdot(w.grad, w.pg);
     gnorm = sqrtf(vdot(w.grad, w.grad));
-    float beta = fmaxf(0.f, (gpn - gpo) / fmaxf(gpg, 1e-30f));
+    float beta = restart ? 0.f : fmaxf(0.f, (gpn - gpo) / fmaxf(gpg, 1e-30f));
     gpg = gpn;
     for (int i = lane; i < nv; i += 32) w.s[i] = -w.pg[i] + beta * w.s[i];
     __syncwarp();
@@ -741,7 +787,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     if (lane < 7) { qv_g[lane] = w.qdarm[lane]; qp_g[lane] += h * w.qdarm[lane]; }
     if (dm.soft) {
       for (int i = lane; i < np; i += 32) {
-        float v = w.vs[i] + h * w.x[13 + i];
+        float v = qv_g[13 + i] + h * w.x[13 + i];
         qv_g[13 + i] = v;
         qp_g[14 + i] = w.qs[i] + h * v;
       }
@@ -849,7 +895,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       for (int j = 0; j < 7; j++) d[13 + j] = w.ab[AB_TAU + j];
       int nlim = 0;
       for (int j = 0; j < 7; j++) nlim += w.lsign[j] != 0.f;
-      d[20] = (float)iters; d[21] = gnorm; d[22] = (float)ncon;
+      d[20] = (float)iters; d[21] = gnorm; d[22] = (float)ncon_found;
       d[23] = (float)(3 * ncon + nlim + (dm.soft ? 2 * 0 + np + dm.npair + 1 : 0));
     }
   }

@@ -48,6 +48,8 @@ struct usim_handle {
   size_t smem = 0;
 };
 
+static usim_handle* g_active = nullptr; // handle whose DevModel currently sits in the constant block
+
 const char* usim_last_error(void) { return g_err.c_str(); }
 int usim_abi_version(void) { return USIM_ABI_VERSION; }
 size_t usim_sizeof_model(void) { return sizeof(usim_model); }
@@ -145,6 +147,7 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   d.mode = c->impedance_mode; d.horizon = c->horizon; d.early_term = c->early_termination;
   d.solref_rand = c->solref_randomization; d.pos_rand = c->probe_pos_randomization; d.det_traj = c->deterministic_trajectory;
   d.uncouple = c->uncouple_pos_ori; d.iters = c->solver_iterations > 0 ? c->solver_iterations : 40;
+  d.max_rebuilds = c->precond_rebuilds > 0 ? c->precond_rebuilds : 8; // preconditioner rebuilds per solve when contact zones change
   d.adim = h->adim; d.env_off = c->env_id_offset; d.nq = m->nq; d.nv = m->nv;
   d.seed_lo = (unsigned)(c->seed & 0xffffffffu); d.seed_hi = (unsigned)(c->seed >> 32);
   d.ctrl_freq = (float)c->control_freq;
@@ -197,7 +200,6 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   CKH(cudaMalloc((void**)&h->d_resetmask, N));
   CKH(cudaMemset(h->d_obs, 0, N * USIM_OBS_DIM * sizeof(float)));
   CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  CKH(cudaMemcpyToSymbol(dm, &h->hm, sizeof(DevModel)));
   h->smem = sizeof(WS) * WARPS_PER_CTA;
   CKH(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   CKH(cudaDeviceSynchronize());
@@ -209,6 +211,7 @@ int usim_destroy(usim_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  if (g_active == h) g_active = nullptr;
   for (auto& p : h->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   void* dev[] = {h->qpos, h->qvel, h->warm, h->task, h->armbuf, h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->part_pos,
                  h->part_axis, h->iw_dof, h->iw_body, h->nbr, h->eq_pairs, h->nbr_pair, h->d_act, h->d_obs, h->d_tobs, h->d_rew,
@@ -224,10 +227,12 @@ int usim_destroy(usim_handle* h) {
 static PartTables tables(const usim_handle* h) { return PartTables{h->part_pos, h->part_axis, h->iw_dof, h->iw_body, h->nbr}; }
 
 // launches: the DevModel symbol is per-process; re-upload if another handle changed it
-static usim_handle* g_active = nullptr;
 static int activate(usim_handle* h) {
   CK(cudaSetDevice(h->device));
   if (g_active != h) {
+    // the contract is one handle per (process, GPU); switching handles is supported but drains the device first,
+    // because kernels of the previous handle may still be reading the constant block
+    CK(cudaDeviceSynchronize());
     CK(cudaMemcpyToSymbol(dm, &h->hm, sizeof(DevModel)));
     g_active = h;
   }

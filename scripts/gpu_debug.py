@@ -64,9 +64,52 @@ def press(s, n):
     return a
 
 
+def sweep():
+    """Accuracy vs solver tolerance / iteration cap: rigid press + random, and soft tracking."""
+    def run(soft, cc, nsteps, act_fn, **kw):
+        n = 2
+        env = BatchedUltrasound(n, soft_torso=soft, controller_configs=cc, control_freq=500, horizon=1000, seed=3, **kw)
+        pk = packed_model(soft)
+        env.reset()
+        q, v, w, t = [x.cpu().numpy().astype(np.float64) for x in env.get_state()]
+        okw = {k: x for k, x in kw.items() if k not in ("solver_iterations", "solver_tolerance")}
+        e = O.OracleEnv(pk, make_config(1, cc, control_freq=500, horizon=1000, seed=3, **okw), 0)
+        e.reset(); e.set_state(q[0], v[0], w[0], t[0])
+        rng = np.random.default_rng(0)
+        lo, hi = env.action_spec
+        mdq = mdv = mdf = 0.0; its = []
+        for s in range(nsteps):
+            a = act_fn(s, n, rng, lo, hi)
+            o, r, dn, _ = env.step(torch.as_tensor(a, dtype=torch.float32), auto_reset=False)
+            oo, orr, od = e.step(a[0])
+            q, v, _, _ = [x.cpu().numpy().astype(np.float64) for x in env.get_state()]
+            oq, ov, _, _ = e.get_state()
+            mdq = max(mdq, np.abs(q[0] - oq).max()); mdv = max(mdv, np.abs(v[0] - ov).max())
+            mdf = max(mdf, abs(float(o[0, 2]) - oo[2]) / max(1.0, abs(oo[2])))
+            its.append(float(env.diag()[0, 20]))
+        env.close()
+        return mdq, mdv, mdf, np.mean(its), np.max(its)
+
+    def press_then_random(s, n, rng, lo, hi):
+        if s < 250:
+            a = np.zeros((n, 6)); a[:, 2] = -1; return a
+        return np.repeat(rng.uniform(lo, hi, size=(1, 6)), n, 0)
+
+    def rnd(s, n, rng, lo, hi):
+        return rng.uniform(lo, hi, size=(n, 6))
+
+    for tol in (1e-5, 3e-6, 1e-6, 3e-7, 1e-7):
+        for cap in (20, 40, 80):
+            r = run(False, CC_FIXED, 400, press_then_random, solver_tolerance=tol, solver_iterations=cap)
+            sft = run(True, CC_TRACK, 60, rnd, solver_tolerance=tol, solver_iterations=cap, torso_solref_randomization=True, initial_probe_pos_randomization=True)
+            print(f"tol {tol:.0e} cap {cap}: rigid dq {r[0]:.2e} dv {r[1]:.2e} dF {r[2]:.2e} it {r[3]:.1f}/{r[4]:.0f} | soft dq {sft[0]:.2e} dv {sft[1]:.2e} dF {sft[2]:.2e} it {sft[3]:.1f}/{sft[4]:.0f}", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     t0 = time.time()
+    if which == "sweep":
+        sweep()
     if which in ("all", "rigid"):
         compare("rigid free-space random", False, CC_FIXED, 30)
         compare("rigid press", False, CC_FIXED, 260, act_fn=press)

@@ -1,0 +1,307 @@
+"""Parity of the CUDA path (through the C ABI) with the float64 oracle, BASELINE configs 2 and 3, plus
+size-independent properties at the full 4096-env size.
+
+Stated tolerances (fp32 kernels vs float64 oracle, SURVEY §8d / BASELINE.md §4):
+  free space         max|dqpos| <= 1e-4 rad, max|dqvel| <= 1e-3 over 250 steps
+  contact force      relative 1e-2 (+5e-2 N absolute) after the first 5 contact steps
+  reward             5e-2 absolute
+  contact pairs      exact (pairs whose oracle distance is within 1e-6 m of the threshold may differ)
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CC_FIXED, CC_TRACK
+from rui_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(n, soft, cc, **kw):
+    from rui_b200.env import BatchedUltrasound
+    return BatchedUltrasound(n, device=0, soft_torso=soft, controller_configs=cc, control_freq=500, horizon=kw.pop("horizon", 1000), **kw)
+
+
+def _oracle_from_gpu(O, env, soft, cc, i, **kw):
+    """Oracle env continuing from the GPU env's current state (identical initial states, as north_star asks)."""
+    from rui_b200.env import packed_model
+    kw = {k: v for k, v in kw.items() if k not in ("solver_iterations", "solver_tolerance")}
+    e = O.OracleEnv(packed_model(soft), abi.make_config(1, cc, control_freq=500, **kw), i)
+    e.reset()
+    q, v, w, t = [x[i].cpu().numpy().astype(np.float64) for x in env.get_state()]
+    e.set_state(q, v, w, t)
+    return e
+
+
+def _np(*xs):
+    return [x.cpu().numpy().astype(np.float64) for x in xs]
+
+
+def _contact_lists_match(env, orc, i):
+    ncon, g1, g2, _ = env.contacts()
+    n = int(ncon[i])
+    got = list(zip(g1[i, :n].tolist(), g2[i, :n].tolist()))
+    c = orc.contacts()
+    want = list(zip(c["geom1"].tolist(), c["geom2"].tolist()))
+    if got == want:
+        return True
+    # a pair may differ only if it sits on the detection threshold (|dist| < 2e-6 m in the oracle, or GPU-only)
+    dist = {p: d for p, d in zip(want, c["dist"])}
+    extra = [p for p in got if p not in dist]
+    missing = [p for p in want if p not in got]
+    common_got = [p for p in got if p in dist and p not in missing]
+    common_want = [p for p in want if p not in missing]
+    return common_got == common_want and all(abs(dist[p]) < 2e-6 for p in missing) and len(extra) <= 1
+
+
+def test_reset_matches_oracle(O):
+    kw = dict(torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=3)
+    env = _make(8, True, CC_TRACK, **kw)
+    obs = env.reset().cpu().numpy()
+    q, v, w, t = _np(*env.get_state())
+    from rui_b200.env import packed_model
+    for i in range(8):
+        e = O.OracleEnv(packed_model(True), abi.make_config(1, CC_TRACK, control_freq=500, **kw), i)
+        oobs = e.reset()
+        oq, ov, ow, ot = e.get_state()
+        # integer Philox draws are bit-exact; the float draws and the IK agree to fp32 round-off
+        assert t[i, abi.TS_STIFFNESS] == ot[abi.TS_STIFFNESS] and t[i, abi.TS_DAMPING] == ot[abi.TS_DAMPING]
+        np.testing.assert_allclose(t[i, :7], ot[:7], atol=2e-7)
+        np.testing.assert_allclose(q[i, :7], oq[:7], atol=2e-5)
+        np.testing.assert_allclose(q[i, 7:], oq[7:], atol=1e-6)
+        assert np.all(v[i] == 0) and np.all(w[i] == 0)
+        np.testing.assert_allclose(obs[i, 12:19], oobs[12:19], atol=2e-5)
+        np.testing.assert_allclose(obs[i, :3], oobs[:3], rtol=2e-2, atol=0.2)  # ~30 N contact force from a ~1 cm penetration
+        assert obs[i, 9] == pytest.approx(obs[i, 2] - 5, abs=1e-5) and obs[i, 10] == 0 and obs[i, 11] == pytest.approx(-0.04)
+    env.close()
+
+
+def test_config2_rigid_press_trajectory_parity(O):
+    """BASELINE config 2: probe press on the rigid table, fixed-gain OSC (main.py:25-44), all envs from init_qpos:
+    250 steps of action (0,0,-1,0,0,0), then 250 seeded random-action steps."""
+    n = 4096
+    env = _make(n, False, CC_FIXED)
+    env.reset()
+    orc = _oracle_from_gpu(O, env, False, CC_FIXED, 0)
+    press = torch.zeros(n, 6)
+    press[:, 2] = -1
+    gen = torch.Generator().manual_seed(3)
+    contact_steps, drift = 0, []
+    for s in range(500):
+        a = press if s < 250 else (torch.rand(1, 6, generator=gen) * 2 - 1).repeat(n, 1)
+        o, r, d, _ = env.step(a, auto_reset=False)
+        oo, orr, od = orc.step(a[0].numpy().astype(np.float64))
+        q, v, _, _ = env.get_state()
+        oq, ov, _, _ = orc.get_state()
+        dq, dv = np.abs(q[0].cpu().numpy() - oq).max(), np.abs(v[0].cpu().numpy() - ov).max()
+        drift.append((dq, dv))
+        assert dq <= 1e-4 and dv <= 1e-3, (s, dq, dv)
+        assert abs(float(r[0]) - orr) <= 5e-2 and bool(d[0]) == od
+        assert _contact_lists_match(env, orc, 0), s
+        if orc.ncon:
+            contact_steps += 1
+            if contact_steps > 5:
+                assert abs(float(o[0, 2]) - oo[2]) <= 1e-2 * abs(oo[2]) + 5e-2, (s, float(o[0, 2]), oo[2])
+        if s in (0, 249, 499):  # every env started identically and received the same actions: bit-identical rows
+            assert bool((q == q[0]).all()) and bool((v == v[0]).all()) and bool((o[:, :9] == o[0, :9]).all())  # (trajectories differ per env)
+    assert contact_steps > 20  # the press really reached the table
+    env.close()
+
+
+def test_config3_soft_sweep_parity(O):
+    """BASELINE config 3 physics: soft-torso composite, tracking controller of rl_config.yaml, random gains."""
+    kw = dict(torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=3)
+    n = 4
+    env = _make(n, True, CC_TRACK, **kw)
+    env.reset()
+    orcs = [_oracle_from_gpu(O, env, True, CC_TRACK, i, **kw) for i in range(n)]
+    rng = np.random.default_rng(0)
+    for s in range(60):
+        a = rng.uniform(0, 1, size=(n, 6))
+        o, r, d, _ = env.step(torch.as_tensor(a, dtype=torch.float32), auto_reset=False)
+        q, v, _, t = _np(*env.get_state())
+        o, r = _np(o, r)
+        for i in range(n):
+            oo, orr, od = orcs[i].step(a[i])
+            oq, ov, _, ot = orcs[i].get_state()
+            assert np.abs(q[i] - oq).max() <= 1e-4 and np.abs(v[i] - ov).max() <= 2e-3, (s, i)
+            assert abs(o[i, 2] - oo[2]) <= 1e-2 * abs(oo[2]) + 5e-2, (s, i, o[i, 2], oo[2])
+            assert abs(r[i] - orr) <= 5e-2 and bool(d[i]) == od
+            np.testing.assert_allclose(o[i, 6:9], oo[6:9], atol=2e-3)
+            np.testing.assert_allclose(o[i, 11:19], oo[11:19], atol=1e-4)
+            np.testing.assert_allclose(t[i, abi.TS_TRAJ_PT:abi.TS_TRAJ_PT + 3], ot[abi.TS_TRAJ_PT:abi.TS_TRAJ_PT + 3], atol=1e-6)
+            assert t[i, abi.TS_TOUCHED] == ot[abi.TS_TOUCHED] and t[i, abi.TS_TIMESTEP] == ot[abi.TS_TIMESTEP]
+            assert _contact_lists_match(env, orcs[i], i), (s, i)
+    env.close()
+
+
+def test_variable_z_and_wrench_modes_match_oracle(O):
+    for mode in ("variable_z", "wrench"):
+        cc = dict(CC_TRACK, impedance_mode=mode)
+        env = _make(2, True, cc, seed=7)
+        env.reset()
+        orc = _oracle_from_gpu(O, env, True, cc, 0, seed=7)
+        lo, hi = env.action_spec
+        rng = np.random.default_rng(1)
+        for s in range(10):
+            a = rng.uniform(lo, hi, size=(2, env.action_dim))
+            o, r, d, _ = env.step(torch.as_tensor(a, dtype=torch.float32), auto_reset=False)
+            oo, orr, od = orc.step(a[0])
+            dg = env.diag()[0].cpu().numpy()
+            np.testing.assert_allclose(dg[13:20], orc.diag()[13:20], atol=5e-3)  # joint torques
+            assert abs(float(r[0]) - orr) <= 5e-2
+        env.close()
+
+
+# ---------------------------------------------------------------------------- full-size properties (4096 envs)
+def test_full_size_determinism_and_invariants():
+    kw = dict(torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=3)
+    outs = []
+    for run in range(2):
+        env = _make(4096, True, CC_TRACK, **kw)
+        env.reset()
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        for s in range(12):
+            o, r, d, _ = env.step(torch.rand(4096, 6, device="cuda", generator=gen), auto_reset=True)
+        q, v, w, t = env.get_state()
+        outs.append((o.clone(), r.clone(), q, v))
+        if run == 0:
+            assert torch.isfinite(o).all() and torch.isfinite(q).all() and torch.isfinite(v).all()
+            assert (r >= 0).all() and (r <= 12).all()  # ultrasound.py:230-269: five terms, maxima 5+1+1+3+2
+            assert ((q[:, 10:14] ** 2).sum(1) - 1).abs().max() < 1e-5  # unit torso quaternion
+            assert (o[:, 15:19] ** 2).sum(1).sub(1).abs().max() < 1e-3  # product of two unit quaternions
+            assert (t[:, abi.TS_TIMESTEP] == 12).all()
+            ncon = env.contacts()[0]
+            assert int(ncon.min()) > 20 and int(ncon.max()) <= abi.MAX_CONTACTS
+            lo = torch.tensor(env.model.g_jnt_range[:, 0], device="cuda")
+            assert (t[:, abi.TS_STIFFNESS] >= 1300).all() and (t[:, abi.TS_STIFFNESS] < 1600).all()
+        env.close()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)  # same seed -> bit-identical, run to run
+
+
+def test_sharding_is_bitwise_invariant():
+    """Rank r of G owns a contiguous slice of global env ids; results do not depend on the split."""
+    kw = dict(torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=3)
+    full = _make(96, True, CC_TRACK, **kw)
+    part = _make(32, True, CC_TRACK, env_id_offset=48, **kw)
+    of, op = full.reset().clone(), part.reset().clone()
+    assert torch.equal(of[48:80], op)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    for s in range(5):
+        a = torch.rand(96, 6, device="cuda", generator=gen)
+        of = full.step(a)[0].clone()
+        op = part.step(a[48:80].contiguous())[0].clone()
+        assert torch.equal(of[48:80], op)
+    full.close(); part.close()
+
+
+def test_auto_reset_and_horizon_semantics():
+    env = _make(64, True, CC_TRACK, horizon=5, seed=1, torso_solref_randomization=True)
+    env.reset()
+    t0 = env.get_state()[3]
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    for s in range(1, 12):
+        o, r, d, tobs = env.step(torch.rand(64, 6, device="cuda", generator=gen), auto_reset=True)
+        t = env.get_state()[3]
+        if s % 5 == 0:
+            assert bool(d.all())
+            assert (t[:, abi.TS_TIMESTEP] == 0).all() and (t[:, abi.TS_EPISODE] == 1 + s // 5).all()
+            assert (o[:, 10] == 0).all() and torch.allclose(o[:, 11], torch.full((64,), -0.04, device="cuda"))  # post-reset obs invariants [ART]
+            assert not torch.equal(tobs, o)  # terminal observation kept separately (SB3 VecEnv semantics)
+            assert not torch.equal(t[:, abi.TS_STIFFNESS], t0[:, abi.TS_STIFFNESS])  # hard reset re-draws the torso solref
+        else:
+            assert not bool(d.any())
+            assert (t[:, abi.TS_TIMESTEP] == s % 5).all()
+    env.close()
+
+
+def test_done_envs_freeze_without_auto_reset_and_masked_reset():
+    env = _make(8, True, CC_TRACK, horizon=3, seed=1)
+    env.reset()
+    a = torch.full((8, 6), 0.5)
+    for s in range(3):
+        o, r, d, _ = env.step(a, auto_reset=False)
+    assert bool(d.all())
+    q0 = env.get_state()[0].clone()
+    o, r, d, _ = env.step(a, auto_reset=False)  # frozen: nothing moves, done reported as 0 (nothing newly finished)
+    assert torch.equal(env.get_state()[0], q0) and not bool(d.any())
+    mask = torch.zeros(8, dtype=torch.uint8)
+    mask[[1, 5]] = 1
+    env.reset(mask)
+    t = env.get_state()[3]
+    assert t[:, abi.TS_DONE].tolist() == [1, 0, 1, 1, 1, 0, 1, 1]
+    assert t[:, abi.TS_EPISODE].tolist() == [1, 2, 1, 1, 1, 2, 1, 1]
+    env.close()
+
+
+def test_early_termination_conditions_fire():
+    """ultrasound.py:635-670 on the device: with random gains some episodes must end early, each for a listed reason."""
+    env = _make(512, True, CC_TRACK, early_termination=True, seed=4, torso_solref_randomization=True, initial_probe_pos_randomization=True)
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    seen = 0
+    lo = torch.tensor(env.model.g_jnt_range[:, 0], device="cuda", dtype=torch.float32)
+    hi = torch.tensor(env.model.g_jnt_range[:, 1], device="cuda", dtype=torch.float32)
+    for s in range(150):
+        o, r, d, _ = env.step(torch.rand(512, 6, device="cuda", generator=gen), auto_reset=False)
+        q, _, _, t = env.get_state()
+        idx = torch.nonzero(d).flatten()
+        for i in idx.tolist()[:8]:
+            pe = float((t[i, abi.TS_POS_ERR] ** 2 + t[i, abi.TS_POS_ERR + 1] ** 2).sqrt())
+            inc, touched, oe = bool(t[i, abi.TS_IN_CONTACT]), bool(t[i, abi.TS_TOUCHED]), float(t[i, abi.TS_ORI_ERR])
+            qlim = bool(((q[i, :7] <= lo + 0.1) | (q[i, :7] >= hi - 0.1)).any())
+            assert qlim or pe > 1.0 or (inc and oe > 0.10) or (touched and not inc), (i, pe, inc, touched, oe)
+            seen += 1
+    assert seen > 0
+    env.close()
+
+
+def test_robosuite_style_api_and_wrappers():
+    from rui_b200.env import GymWrapper, UltrasoundVecEnv, make, PROPRIO_KEY, SENSOR_NAMES
+    env = make("Ultrasound", robots="Panda", controller_configs=CC_TRACK, control_freq=500, horizon=4, use_camera_obs=False,
+               use_object_obs=False, has_renderer=False, has_offscreen_renderer=False, early_termination=False, seed=3)
+    with pytest.raises(ValueError, match="terminated episode"):
+        env.step(np.zeros(6))
+    od = env.reset()
+    assert list(od.keys()) == [n for n, _ in SENSOR_NAMES] + [PROPRIO_KEY] and od[PROPRIO_KEY].shape == (19,)
+    assert np.array_equal(np.concatenate([od[n] for n, _ in SENSOR_NAMES]), od[PROPRIO_KEY])
+    lo, hi = env.action_spec
+    assert lo.tolist() == [0] * 6 and hi.tolist() == [1] * 6
+    for s in range(4):
+        od, r, d, info = env.step(np.full(6, 0.6))
+        assert isinstance(r, float) and isinstance(d, bool) and info == {}
+    assert d and env.timestep == 4
+    with pytest.raises(ValueError):
+        env.step(np.zeros(6))
+    assert isinstance(env._check_probe_contact_with_torso(), bool)
+    assert env.robots[0]._joint_positions.shape == (7,) and env.robots[0].torques.shape == (7,) and env.robots[0].ee_torque.shape == (3,)
+    env.close()
+    g = GymWrapper(make("Ultrasound", robots="Panda", controller_configs=CC_TRACK, control_freq=500, horizon=3, use_camera_obs=False))
+    assert g.observation_space.shape == (19,) and g.action_space.shape == (6,)
+    ob = g.reset()
+    assert ob.shape == (19,)
+    ob, r, d, info = g.step(g.action_space.sample(np.random.default_rng(0)))
+    assert ob.shape == (19,)
+    g.close()
+    ve = UltrasoundVecEnv(16, dict(controller_configs=CC_TRACK, control_freq=500, horizon=3, early_termination=False), seed=3)
+    ob = ve.reset()
+    assert ob.shape == (16, 19) and ob.dtype == np.float32
+    for s in range(3):
+        ob, rew, dn, infos = ve.step(np.random.default_rng(s).uniform(-1, 2, size=(16, 6)))  # out-of-range actions get clipped
+    assert dn.all() and all("terminal_observation" in i and i["episode"]["l"] == 3 for i in infos)
+    assert all(0 <= i["episode"]["r"] <= 36 for i in infos)
+    ve.close()
+    with pytest.raises(NotImplementedError):
+        make("Ultrasound", robots="Panda", controller_configs=CC_TRACK, control_freq=500, use_camera_obs=True)
+    with pytest.raises(Exception, match="not found"):
+        make("Lift")
+
+
+def test_create_rejects_bad_arguments():
+    from rui_b200._lib import UsimError
+    from rui_b200.env import BatchedUltrasound
+    with pytest.raises(UsimError, match="control_freq"):
+        BatchedUltrasound(4, controller_configs=CC_TRACK, control_freq=20)  # 25 substeps: not built (rl_config uses 500 Hz)
+    with pytest.raises(UsimError, match="num_envs"):
+        BatchedUltrasound(0, controller_configs=CC_TRACK, control_freq=500)
