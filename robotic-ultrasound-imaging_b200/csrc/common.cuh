@@ -125,6 +125,28 @@ __device__ __forceinline__ bool chol(float* A) {
   }
   return ok;
 }
+// rolled variant for rarely executed code (small SASS): A in shared/global memory
+__device__ __noinline__ bool chol_rolled(float* A, int n) {
+  bool ok = true;
+#pragma unroll 1
+  for (int j = 0; j < n; j++) {
+    float s = A[j * n + j];
+#pragma unroll 1
+    for (int k = 0; k < j; k++) s -= A[j * n + k] * A[j * n + k];
+    if (!(s > 0.f)) { ok = false; s = 1e-20f; }
+    s = sqrtf(s);
+    A[j * n + j] = s;
+    float inv = 1.f / s;
+#pragma unroll 1
+    for (int i = j + 1; i < n; i++) {
+      float t = A[i * n + j];
+#pragma unroll 1
+      for (int k = 0; k < j; k++) t -= A[i * n + k] * A[j * n + k];
+      A[i * n + j] = t * inv;
+    }
+  }
+  return ok;
+}
 template <int N>
 __device__ __forceinline__ void chol_solve(const float* L, float* x) {
 #pragma unroll

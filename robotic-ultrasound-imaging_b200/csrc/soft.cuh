@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
   }
   if (dm.soft) {
     const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
     for (int pass = 0; pass < 2; pass++) { // pass 0: (table, particle k); pass 1: (probe, particle k)
       for (int base = 0; base < np; base += 32) {
         int i = base + lane;
@@ -503,129 +504,108 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
   };
   auto vdot = [&](const float* a, const float* b) {
     float s = 0.f;
+#pragma unroll 1
     for (int i = lane; i < nv; i += 32) s += a[i] * b[i];
     return wsum(s);
   };
 
-  // ------------------------------------------------------------------ K6: initial point = warm start
-  applyH(w.x, w.Hx);
-  const float rhsn = sqrtf(vdot(w.grad, w.grad));
-  for (int i = lane; i < nv; i += 32) w.Hx[i] -= w.grad[i];
+  // ------------------------------------------------------------------ K6: nonlinear PCG; pass -1 evaluates the warm start
   for (int c = lane; c < ncon; c += 32) w.czone[c] = 255; // "unknown": the first update always reports a change
+  for (int i = lane; i < QPAD; i += 32) w.s[i] = 0.f;
   __syncwarp();
-  dense_vel(w.x);
-  contactJ(w.x, w.cjar, true);
-  update_grad();
 
   // preconditioner from the current active set (contact zones); rebuilt when the zones change
   auto build_precond = [&]() {
+    // Runs 1-3 times per solve: written for SMALL CODE (rolled loops, stack arrays), not for speed, so that it does not
+    // evict the CG loop body from the instruction cache.
+#pragma unroll 1
     for (int i = lane; i < np; i += 32) { w.dg[i] = w.dg0[i]; w.kx[i] = 0.f; w.ky[i] = 0.f; w.kz[i] = 0.f; }
     __syncwarp();
-    float kf[21], kp[21];
+    float acc[42]; // packed upper triangles of the 6x6 wrench-space Hessians: [0..20] torso side (about P), [21..41] probe side (about the site)
 #pragma unroll
-    for (int k = 0; k < 21; k++) { kf[k] = 0.f; kp[k] = 0.f; }
+    for (int k = 0; k < 42; k++) acc[k] = 0.f;
+#pragma unroll 1
     for (int c = lane; c < ncon; c += 32) {
       int zone = w.czone[c], type = w.ctype[c], i = w.cpart[c];
       if (zone == 0) continue;
       float Dn = w.cD[c];
-      v3 nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]);
-      // world-frame 3x3 contact Hessian K = F^T H F (F = contact frame rows, H = Hessian of the cone cost wrt jar)
-      float Km[9];
-      float nv3[3] = {nn.x, nn.y, nn.z};
-      if (zone == 2) { // bottom zone: H = diag(Dn, Dt, Dt)  ->  K = Dt I + (Dn - Dt) n n^T
-        float Dtg = Dn * dm.impratio;
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-          for (int b = 0; b < 3; b++) Km[3 * a + b] = (a == b ? Dtg : 0.f) + (Dn - Dtg) * nv3[a] * nv3[b];
+      v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]);
+      float F[9]; // contact frame rows: normal, tangent 1, tangent 2
+      {
+        v3 nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), t1, t2;
+        make_frame(nn, &t1, &t2);
+        st3(F, nn); st3(F + 3, t1); st3(F + 6, t2);
+      }
+      float Hc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // Hessian of the cone cost wrt (jar_n, jar_t1, jar_t2)
+      if (zone == 2) { // bottom zone: quadratic
+        Hc[0] = Dn; Hc[4] = Dn * dm.impratio; Hc[8] = Dn * dm.impratio;
       } else { // middle zone: exact Hessian of 0.5 Dm (N - mu T)^2
         float fr, mu;
         contact_params(type, fr, mu);
-        v3 t1, t2;
-        make_frame(nn, &t1, &t2);
         float N = w.cjar[0][c] * mu, U1 = w.cjar[1][c] * fr, U2 = w.cjar[2][c] * fr, T = fmaxf(sqrtf(U1 * U1 + U2 * U2), 1e-20f);
         float Dm = Dn / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T, u1 = U1 / T, u2 = U2 / T;
-        float g3[3] = {1.f, -mu * u1, -mu * u2}, sc[3] = {mu, fr, fr}, kk = -Dm * mu * NmT / T;
-        float H3[9];
+        float g3[3] = {mu, -mu * u1 * fr, -mu * u2 * fr}, kk = -Dm * mu * NmT / T * fr * fr;
 #pragma unroll
-        for (int a = 0; a < 3; a++)
+        for (int a2 = 0; a2 < 3; a2++)
 #pragma unroll
-          for (int b = 0; b < 3; b++) H3[3 * a + b] = Dm * g3[a] * g3[b];
-        H3[4] += kk * (1.f - u1 * u1); H3[5] -= kk * u1 * u2; H3[7] -= kk * u1 * u2; H3[8] += kk * (1.f - u2 * u2);
-        float Fm[9] = {nn.x, nn.y, nn.z, t1.x, t1.y, t1.z, t2.x, t2.y, t2.z};
-#pragma unroll
-        for (int a = 0; a < 9; a++) Km[a] = 0.f;
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-          for (int b = 0; b < 3; b++) {
-            float hab = sc[a] * H3[3 * a + b] * sc[b];
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-              for (int q = 0; q < 3; q++) Km[3 * r + q] += hab * Fm[3 * a + r] * Fm[3 * b + q];
-          }
+          for (int b2 = 0; b2 < 3; b2++) Hc[3 * a2 + b2] = Dm * g3[a2] * g3[b2];
+        Hc[4] += kk * (1.f - u1 * u1); Hc[5] -= kk * u1 * u2; Hc[7] -= kk * u1 * u2; Hc[8] += kk * (1.f - u2 * u2);
       }
-      for (int side = 0; side < 2; side++) {
-        if (side == 0 && type == 2) continue;
-        if (side == 1 && type == 0) continue;
-        v3 r = side == 0 ? pos - P : pos - site;
-        // A = [I, -[r]x] ; H = A^T K A ; upper triangle, row-major packed
-        float X[9] = {0, -r.z, r.y, r.z, 0, -r.x, -r.y, r.x, 0}, KX[9], XtKX[9];
-        mm3(Km, X, KX); // K [r]x
-        float Xt[9] = {X[0], X[3], X[6], X[1], X[4], X[7], X[2], X[5], X[8]};
-        mm3(Xt, KX, XtKX);
-        float H[36];
+      if (type != 2) { // slider of this particle: k_i += K a_i, dg_i += a_i^T K a_i with K = F^T Hc F
+        v3 aw = mv(R, ld3(pt.axis + 3 * i));
+        v3 fa = mv(F, aw), hf = mv(Hc, fa), ka = mtv(F, hf);
+        atomicAdd(&w.kx[i], ka.x); atomicAdd(&w.ky[i], ka.y); atomicAdd(&w.kz[i], ka.z);
+        atomicAdd(&w.dg[i], dot(fa, hf));
+      }
+      // wrench-space Hessian A^T K A with A = [I, -[r]x]: W[a] = [f_a ; r x f_a], U = Hc W, acc += W^T U (upper triangle)
+      auto accum = [&](float* A21, v3 r) {
+        float W[18], U[18];
 #pragma unroll
-        for (int a = 0; a < 3; a++)
+        for (int a2 = 0; a2 < 3; a2++) {
+          v3 f = ld3(F + 3 * a2), m3 = cross(r, f);
+          st3(W + 6 * a2, f); st3(W + 6 * a2 + 3, m3);
+        }
 #pragma unroll
-          for (int b = 0; b < 3; b++) {
-            H[a * 6 + b] = Km[3 * a + b];
-            H[a * 6 + 3 + b] = -KX[3 * a + b];
-            H[(3 + a) * 6 + 3 + b] = XtKX[3 * a + b];
-          }
-        float* acc = side == 0 ? kf : kp;
+        for (int a2 = 0; a2 < 3; a2++)
+#pragma unroll
+          for (int q = 0; q < 6; q++) U[6 * a2 + q] = Hc[3 * a2] * W[q] + Hc[3 * a2 + 1] * W[6 + q] + Hc[3 * a2 + 2] * W[12 + q];
         int idx = 0;
 #pragma unroll
-        for (int a = 0; a < 6; a++)
+        for (int p2 = 0; p2 < 6; p2++)
 #pragma unroll
-          for (int b = a; b < 6; b++) acc[idx++] += H[a * 6 + b];
-      }
-      if (type != 2) {
-        v3 aw = mv(R, ld3(pt.axis + 3 * i));
-        v3 ka = mv(Km, aw);
-        atomicAdd(&w.kx[i], ka.x); atomicAdd(&w.ky[i], ka.y); atomicAdd(&w.kz[i], ka.z);
-        atomicAdd(&w.dg[i], dot(aw, ka));
-      }
+          for (int q = p2; q < 6; q++) { A21[idx] += W[p2] * U[q] + W[6 + p2] * U[6 + q] + W[12 + p2] * U[12 + q]; idx++; }
+      };
+      if (type != 2) accum(acc, pos - P);
+      if (type != 0) accum(acc + 21, pos - site);
     }
 #pragma unroll
-    for (int k = 0; k < 21; k++) { kf[k] = wsum(kf[k]); kp[k] = wsum(kp[k]); }
+    for (int k = 0; k < 42; k++) acc[k] = wsum(acc[k]);
     __syncwarp();
-    // arm block: Pa = M + Jsite^T Kp Jsite + limits
-    {
+    // arm block: Pa = M + Jsite^T Kp Jsite + limits   (lanes 0..6, column `lane`)
+    if (lane < 7) {
       float Kp6[36];
-      int idx = 0;
+      {
+        int idx = 21;
 #pragma unroll
-      for (int a = 0; a < 6; a++)
+        for (int a2 = 0; a2 < 6; a2++)
 #pragma unroll
-        for (int b = a; b < 6; b++) { Kp6[a * 6 + b] = kp[idx]; Kp6[b * 6 + a] = kp[idx]; idx++; }
-      if (lane < 7) {
-        float KJ[6]; // (Kp Jsite)[:, lane]
+          for (int b2 = a2; b2 < 6; b2++) { Kp6[a2 * 6 + b2] = acc[idx]; Kp6[b2 * 6 + a2] = acc[idx]; idx++; }
+      }
+      float KJ[6]; // (Kp Jsite)[:, lane]
 #pragma unroll
-        for (int a = 0; a < 6; a++) {
-          float s = 0.f;
+      for (int a2 = 0; a2 < 6; a2++) {
+        float sacc = 0.f;
 #pragma unroll
-          for (int b = 0; b < 6; b++) s += Kp6[a * 6 + b] * w.ab[AB_JSITE + b * 7 + lane];
-          KJ[a] = s;
-        }
+        for (int b2 = 0; b2 < 6; b2++) sacc += Kp6[a2 * 6 + b2] * w.ab[AB_JSITE + b2 * 7 + lane];
+        KJ[a2] = sacc;
+      }
 #pragma unroll
-        for (int r = 0; r < 7; r++) {
-          float s = w.ab[AB_M + r * 7 + lane];
+      for (int r2 = 0; r2 < 7; r2++) {
+        float sacc = w.ab[AB_M + r2 * 7 + lane];
 #pragma unroll
-          for (int a = 0; a < 6; a++) s += w.ab[AB_JSITE + a * 7 + r] * KJ[a];
-          if (r == lane && w.lsign[lane] != 0.f) s += w.lD[lane];
-          w.Pa[r * 7 + lane] = s;
-        }
+        for (int a2 = 0; a2 < 6; a2++) sacc += w.ab[AB_JSITE + a2 * 7 + r2] * KJ[a2];
+        if (r2 == lane && w.lsign[lane] != 0.f) sacc += w.lD[lane];
+        w.Pa[r2 * 7 + lane] = sacc;
       }
     }
     // torso block: Sf = Mff + Kf(local) - sum_i b_i b_i^T / dg_i
@@ -633,111 +613,138 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       float sb[21];
 #pragma unroll
       for (int k = 0; k < 21; k++) sb[k] = 0.f;
+#pragma unroll 1
       for (int i = lane; i < np; i += 32) {
         v3 ah = ld3(pt.axis + 3 * i), aw = mv(R, ah);
         v3 kk = mk(w.kx[i], w.ky[i], w.kz[i]);
         v3 bv = kk + dm.part_mass * aw;
         v3 cr = mv(R, ld3(pt.pos + 3 * i) + (w.qs[i] - dm.cap_r) * ah);
         v3 bw = mtv(R, cross(cr, kk));
-        float b[6] = {bv.x, bv.y, bv.z, bw.x, bw.y, bw.z}, inv = 1.f / w.dg[i];
+        float b6[6] = {bv.x, bv.y, bv.z, bw.x, bw.y, bw.z}, inv = 1.f / w.dg[i];
         int idx = 0;
 #pragma unroll
-        for (int a = 0; a < 6; a++)
+        for (int a2 = 0; a2 < 6; a2++)
 #pragma unroll
-          for (int c2 = a; c2 < 6; c2++) sb[idx++] += b[a] * b[c2] * inv;
+          for (int c2 = a2; c2 < 6; c2++) { sb[idx] += b6[a2] * b6[c2] * inv; idx++; }
       }
 #pragma unroll
       for (int k = 0; k < 21; k++) sb[k] = wsum(sb[k]);
       if (lane == 0) {
-        float Kf[36];
+        // rotate the angular part of Kf to the body frame: T = diag(I, R); Kl = T^T Kf T.  Scratch: hs[0..95] (dead here)
+        float* Kf = w.hs; float* Kl = w.hs + 36; float* sbs = w.hs + 72;
+        {
+          int idx = 0;
+#pragma unroll
+          for (int a2 = 0; a2 < 6; a2++)
+#pragma unroll
+            for (int b2 = a2; b2 < 6; b2++) { Kf[a2 * 6 + b2] = acc[idx]; Kf[b2 * 6 + a2] = acc[idx]; sbs[idx] = sb[idx]; idx++; }
+        }
         int idx = 0;
-        for (int a = 0; a < 6; a++)
-          for (int b = a; b < 6; b++) { Kf[a * 6 + b] = kf[idx]; Kf[b * 6 + a] = kf[idx]; idx++; }
-        // rotate the angular part to the body frame: T = diag(I, R); Kl = T^T Kf T
-        float Kl[36];
-        for (int a = 0; a < 3; a++)
-          for (int b = 0; b < 3; b++) {
-            Kl[a * 6 + b] = Kf[a * 6 + b];
+#pragma unroll 1
+        for (int a2 = 0; a2 < 3; a2++)
+#pragma unroll 1
+          for (int b2 = 0; b2 < 3; b2++) {
+            Kl[a2 * 6 + b2] = Kf[a2 * 6 + b2];
             float s1 = 0.f, s2 = 0.f;
-            for (int k = 0; k < 3; k++) s1 += Kf[a * 6 + 3 + k] * R[3 * k + b];
-            Kl[a * 6 + 3 + b] = s1; Kl[(3 + b) * 6 + a] = s1;
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) s1 += Kf[a2 * 6 + 3 + k] * w.R[3 * k + b2];
+            Kl[a2 * 6 + 3 + b2] = s1; Kl[(3 + b2) * 6 + a2] = s1;
+#pragma unroll 1
             for (int k = 0; k < 3; k++)
-              for (int l = 0; l < 3; l++) s2 += R[3 * k + a] * Kf[(3 + k) * 6 + 3 + l] * R[3 * l + b];
-            Kl[(3 + a) * 6 + 3 + b] = s2;
+#pragma unroll 1
+              for (int l = 0; l < 3; l++) s2 += w.R[3 * k + a2] * Kf[(3 + k) * 6 + 3 + l] * w.R[3 * l + b2];
+            Kl[(3 + a2) * 6 + 3 + b2] = s2;
           }
-        idx = 0;
-        for (int a = 0; a < 6; a++)
-          for (int b = a; b < 6; b++) {
-            float v = w.Mff[a * 6 + b] + Kl[a * 6 + b] - sb[idx++];
-            w.Sf[a * 6 + b] = v; w.Sf[b * 6 + a] = v;
-          }
-        if (!chol<6>(w.Sf)) { // fall back to the unconditioned free block
-          for (int a = 0; a < 36; a++) w.Sf[a] = w.Mff[a] + Kl[a];
-          chol<6>(w.Sf);
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2; attempt++) {
+          idx = 0;
+#pragma unroll 1
+          for (int a2 = 0; a2 < 6; a2++)
+#pragma unroll 1
+            for (int b2 = a2; b2 < 6; b2++) {
+              float v = w.Mff[a2 * 6 + b2] + Kl[a2 * 6 + b2] - (attempt == 0 ? sbs[idx] : 0.f);
+              idx++;
+              w.Sf[a2 * 6 + b2] = v; w.Sf[b2 * 6 + a2] = v;
+            }
+          if (chol_rolled(w.Sf, 6)) break;
+          // fall back to the free block without the slider coupling
+#pragma unroll 1
           for (int i = 0; i < np; i++) { w.kx[i] = 0.f; w.ky[i] = 0.f; w.kz[i] = 0.f; }
         }
       }
     }
     __syncwarp();
-    if (lane == 0) chol<7>(w.Pa);
+    if (lane == 0) chol_rolled(w.Pa, 7);
     __syncwarp();
   };
-  build_precond();
-  int rebuilds = 0;
 
-  precond();
-  for (int i = lane; i < QPAD; i += 32) w.s[i] = i < nv ? -w.pg[i] : 0.f;
-  __syncwarp();
-  float gpg = vdot(w.grad, w.pg);
-  float gnorm = sqrtf(vdot(w.grad, w.grad));
-  int iters = 0;
+  float gpg = 1.f, gnorm = 0.f, rhsn = 0.f;
+  int iters = 0, rebuilds = 0;
   const int maxit = mode == 1 ? 2 * dm.iters : dm.iters;
-  for (int it = 0; it < maxit; it++) {
-    // fp32 floor of the gradient is ~eps * (|Hx| + |rhs|): the terms that cancel in it
-    if (gnorm <= dm.tol * (1.f + rhsn + sqrtf(vdot(w.Hx, w.Hx)))) break;
-    iters = it + 1;
-    applyH(w.s, w.hs);
-    dense_vel(w.s);
-    contactJ(w.s, w.cjv, false);
-    // ---- exact line search: Newton on phi'(alpha)
-    float q1 = 0.f, q2 = 0.f;
-    for (int i = lane; i < nv; i += 32) { q1 += w.s[i] * w.Hx[i]; q2 += w.s[i] * w.hs[i]; }
-    q1 = wsum(q1); q2 = wsum(q2);
-    float alpha = 0.f, lo = 0.f, hi = -1.f, d0abs = 0.f;
-    for (int ls = 0; ls < 8; ls++) {
-      float d1 = 0.f, d2 = 0.f;
+  // every helper has exactly ONE call site (code size: the loop body must stay inside the instruction cache)
+#pragma unroll 1
+  for (int it = -1; it < maxit; it++) {
+    const bool init = it < 0;
+    if (!init) {
+      // fp32 floor of the gradient is ~eps * (|Hx| + |rhs|): the terms that cancel in it
+      if (gnorm <= dm.tol * (1.f + rhsn + sqrtf(vdot(w.Hx, w.Hx)))) break;
+      iters = it + 1;
+    }
+    const float* vin = init ? w.x : w.s;
+    float* vout = init ? w.Hx : w.hs;
+    applyH(vin, vout);
+    dense_vel(vin);
+    contactJ(vin, init ? w.cjar : w.cjv, init);
+    if (init) {
+      rhsn = sqrtf(vdot(w.grad, w.grad)); // grad holds rhs until here
+      for (int i = lane; i < nv; i += 32) w.Hx[i] -= w.grad[i];
+      __syncwarp();
+    } else {
+      // ---- exact line search: Newton on phi'(alpha)
+      float q1 = 0.f, q2 = 0.f;
+      for (int i = lane; i < nv; i += 32) { q1 += w.s[i] * w.Hx[i]; q2 += w.s[i] * w.hs[i]; }
+      q1 = wsum(q1); q2 = wsum(q2);
+      float alpha = 0.f, lo = 0.f, hi = -1.f, d0abs = 0.f;
+#pragma unroll 1
+      for (int ls = 0; ls < 8; ls++) {
+        float d1 = 0.f, d2 = 0.f;
+        for (int c = lane; c < ncon; c += 32) {
+          float fr, mu, a1, a2, Dn = w.cD[c];
+          contact_params(w.ctype[c], fr, mu);
+          cone_ls(w.cjar[0][c] + alpha * w.cjv[0][c], w.cjar[1][c] + alpha * w.cjv[1][c], w.cjar[2][c] + alpha * w.cjv[2][c],
+                  w.cjv[0][c], w.cjv[1][c], w.cjv[2][c], Dn, Dn * dm.impratio, mu, fr, a1, a2);
+          d1 += a1; d2 += a2;
+        }
+        if (lane < 7 && w.lsign[lane] != 0.f) {
+          float sg = w.lsign[lane], jar = sg * (w.x[lane] + alpha * w.s[lane]) - w.laref[lane], jv = sg * w.s[lane];
+          if (jar < 0.f) { d1 += w.lD[lane] * jar * jv; d2 += w.lD[lane] * jv * jv; }
+        }
+        d1 = wsum(d1) + q1 + alpha * q2;
+        d2 = wsum(d2) + q2;
+        if (ls == 0) d0abs = fabsf(d1);
+        if (fabsf(d1) <= 1e-5f * d0abs || !(d2 > 0.f)) break;
+        if (d1 < 0.f) lo = alpha; else hi = alpha;
+        float an = alpha - d1 / d2;
+        if (hi < 0.f) { if (an <= lo) an = 2.f * alpha + 1e-6f; }
+        else if (an <= lo || an >= hi) an = 0.5f * (lo + hi);
+        if (an == alpha) break;
+        alpha = an;
+      }
+      for (int i = lane; i < nv; i += 32) { w.x[i] += alpha * w.s[i]; w.Hx[i] += alpha * w.hs[i]; }
       for (int c = lane; c < ncon; c += 32) {
-        float fr, mu, a1, a2, Dn = w.cD[c];
-        contact_params(w.ctype[c], fr, mu);
-        cone_ls(w.cjar[0][c] + alpha * w.cjv[0][c], w.cjar[1][c] + alpha * w.cjv[1][c], w.cjar[2][c] + alpha * w.cjv[2][c],
-                w.cjv[0][c], w.cjv[1][c], w.cjv[2][c], Dn, Dn * dm.impratio, mu, fr, a1, a2);
-        d1 += a1; d2 += a2;
+        w.cjar[0][c] += alpha * w.cjv[0][c]; w.cjar[1][c] += alpha * w.cjv[1][c]; w.cjar[2][c] += alpha * w.cjv[2][c];
       }
-      if (lane < 7 && w.lsign[lane] != 0.f) {
-        float sg = w.lsign[lane], jar = sg * (w.x[lane] + alpha * w.s[lane]) - w.laref[lane], jv = sg * w.s[lane];
-        if (jar < 0.f) { d1 += w.lD[lane] * jar * jv; d2 += w.lD[lane] * jv * jv; }
-      }
-      d1 = wsum(d1) + q1 + alpha * q2;
-      d2 = wsum(d2) + q2;
-      if (ls == 0) d0abs = fabsf(d1);
-      if (fabsf(d1) <= 1e-5f * d0abs || !(d2 > 0.f)) break;
-      if (d1 < 0.f) lo = alpha; else hi = alpha;
-      float an = alpha - d1 / d2;
-      if (hi < 0.f) { if (an <= lo) an = 2.f * alpha + 1e-6f; }
-      else if (an <= lo || an >= hi) an = 0.5f * (lo + hi);
-      if (an == alpha) break;
-      alpha = an;
+      __syncwarp();
     }
-    for (int i = lane; i < nv; i += 32) { w.x[i] += alpha * w.s[i]; w.Hx[i] += alpha * w.hs[i]; }
-    for (int c = lane; c < ncon; c += 32) {
-      w.cjar[0][c] += alpha * w.cjv[0][c]; w.cjar[1][c] += alpha * w.cjv[1][c]; w.cjar[2][c] += alpha * w.cjv[2][c];
-    }
-    __syncwarp();
     bool changed = update_grad();
-    float gpo = vdot(w.grad, w.pg); // with the previous pg (Polak-Ribiere)
-    bool restart = false;
+    float gpo = init ? 0.f : vdot(w.grad, w.pg); // with the previous pg (Polak-Ribiere)
+    bool restart = init;
     // soft scene: rebuild when the active set moved; rigid scene (7 unknowns): exact Hessian every iteration = Newton
-    if ((changed && rebuilds < dm.max_rebuilds) || (!dm.soft && ncon > 0)) { build_precond(); rebuilds++; restart = true; }
+    if (init || (changed && rebuilds < dm.max_rebuilds) || (!dm.soft && ncon > 0)) {
+      build_precond();
+      rebuilds += init ? 0 : 1;
+      restart = true;
+    }
     precond();
     float gpn = vdot(w.grad, w.pg);
     gnorm = sqrtf(vdot(w.grad, w.grad));
