@@ -1,0 +1,376 @@
+"""PPO driver for the batched Ultrasound env — the caller side of the hot path (rl.py, BASELINE config 5).
+
+Mirrors what ``rl.py:130-167`` does with stable-baselines3 (not installed here), with the
+hyper-parameters decoded from the shipped models (SURVEY §6 / App. C.6 [ART]):
+``PPO("MlpPolicy", net_arch=[dict(pi=[256,128], vf=[256,128])])``, tanh MLPs, state-independent ``log_std``,
+lr 3e-4 (Adam eps 1e-5), gamma 0.99, GAE lambda 0.95, clip 0.2, ent 0, vf 0.5, max-grad-norm 0.5, 10 epochs,
+``VecNormalize(clip_obs=10, clip_reward=10, gamma=0.99, epsilon=1e-8)``.
+
+Everything stays on the device: the env is stepped through the device-pointer C ABI, the rollout buffer, the
+normaliser and the policy are CUDA tensors.  Multi-GPU: one process per GPU, each rank owns a contiguous slice of
+the global env ids; NCCL is used ONLY for (a) the flat gradient all-reduce per optimiser step, (b) the merge of the
+normaliser moments and episode statistics once per rollout, (c) the initial parameter broadcast.
+
+Documented deviations from SB3 1.1.0a5: with thousands of envs ``n_steps`` must shrink (2048 x 65536 > total
+timesteps) and the minibatch grows with the batch (``batch_size`` is a parameter; SB3's 64 is kept as the default
+only for num_envs <= 64); the running normalisers are updated once per rollout from the merged batch moments
+instead of once per env step (identical statistics, frozen within a rollout).
+"""
+from __future__ import annotations
+
+import io
+import json
+import math
+import os
+import pickle
+import time
+import zipfile
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .dist import allreduce_episode_stats, allreduce_moments
+
+SB3_VERSION = "1.1.0a5"
+
+
+class RunningMeanStd:
+    """SB3 ``RunningMeanStd`` (parallel-variance update) on torch tensors."""
+
+    def __init__(self, shape=(), device="cpu", epsilon: float = 1e-4):
+        self.mean = torch.zeros(shape, dtype=torch.float64, device=device)
+        self.var = torch.ones(shape, dtype=torch.float64, device=device)
+        self.count = torch.tensor(epsilon, dtype=torch.float64, device=device)
+
+    def update_from_moments(self, batch_mean, batch_var, batch_count):
+        delta = batch_mean - self.mean
+        tot = self.count + batch_count
+        new_mean = self.mean + delta * batch_count / tot
+        m2 = self.var * self.count + batch_var * batch_count + delta * delta * self.count * batch_count / tot
+        self.mean, self.var, self.count = new_mean, m2 / tot, tot
+
+    def update(self, x: torch.Tensor, sync: bool = False):
+        x = x.reshape(-1, *self.mean.shape).to(torch.float64)
+        n = torch.tensor(float(x.shape[0]), dtype=torch.float64, device=x.device)
+        mean = x.mean(0)
+        m2 = ((x - mean) ** 2).sum(0)
+        if sync:
+            n, mean, m2 = allreduce_moments(n, mean, m2)
+        self.update_from_moments(mean, m2 / n, n)
+
+    def state(self):
+        return {"mean": self.mean.cpu().numpy(), "var": self.var.cpu().numpy(), "count": float(self.count)}
+
+    def load(self, st):
+        dev = self.mean.device
+        self.mean = torch.as_tensor(np.asarray(st["mean"]), dtype=torch.float64, device=dev).reshape(self.mean.shape)
+        self.var = torch.as_tensor(np.asarray(st["var"]), dtype=torch.float64, device=dev).reshape(self.var.shape)
+        self.count = torch.tensor(float(st["count"]), dtype=torch.float64, device=dev)
+
+
+class VecNormalizeState:
+    """Observation / reward normalisation with SB3 ``VecNormalize`` semantics."""
+
+    def __init__(self, num_envs, obs_dim, device, gamma=0.99, clip_obs=10.0, clip_reward=10.0, epsilon=1e-8):
+        self.obs_rms = RunningMeanStd((obs_dim,), device)
+        self.ret_rms = RunningMeanStd((), device)
+        self.returns = torch.zeros(num_envs, dtype=torch.float64, device=device)
+        self.gamma, self.clip_obs, self.clip_reward, self.epsilon = gamma, clip_obs, clip_reward, epsilon
+        self.training, self.norm_reward = True, True
+
+    def normalize_obs(self, obs):
+        o = (obs.to(torch.float64) - self.obs_rms.mean) / torch.sqrt(self.obs_rms.var + self.epsilon)
+        return torch.clamp(o, -self.clip_obs, self.clip_obs).to(torch.float32)
+
+    def normalize_reward(self, rew):
+        if not self.norm_reward:
+            return rew
+        r = rew.to(torch.float64) / torch.sqrt(self.ret_rms.var + self.epsilon)
+        return torch.clamp(r, -self.clip_reward, self.clip_reward).to(torch.float32)
+
+    def state(self):
+        return {"obs_rms": self.obs_rms.state(), "ret_rms": self.ret_rms.state(), "gamma": self.gamma, "clip_obs": self.clip_obs,
+                "clip_reward": self.clip_reward, "epsilon": self.epsilon}
+
+    def load(self, st):
+        self.obs_rms.load(st["obs_rms"])
+        self.ret_rms.load(st["ret_rms"])
+        self.gamma, self.clip_obs, self.clip_reward = st.get("gamma", 0.99), st.get("clip_obs", 10.0), st.get("clip_reward", 10.0)
+
+
+class MlpPolicy(nn.Module):
+    """SB3 ``ActorCriticPolicy`` with ``net_arch=[dict(pi=[256,128], vf=[256,128])]``; state_dict keys match SB3's."""
+
+    def __init__(self, obs_dim=19, act_dim=6, pi=(256, 128), vf=(256, 128), log_std_init=0.0):
+        super().__init__()
+
+        def mlp(sizes):
+            layers, d = [], obs_dim
+            for h in sizes:
+                layers += [nn.Linear(d, h), nn.Tanh()]
+                d = h
+            return nn.Sequential(*layers)
+
+        self.mlp_extractor = nn.Module()
+        self.mlp_extractor.policy_net = mlp(pi)
+        self.mlp_extractor.value_net = mlp(vf)
+        self.action_net = nn.Linear(pi[-1], act_dim)
+        self.value_net = nn.Linear(vf[-1], 1)
+        self.log_std = nn.Parameter(torch.ones(act_dim) * log_std_init)
+        for mod, gain in ((self.mlp_extractor.policy_net, math.sqrt(2)), (self.mlp_extractor.value_net, math.sqrt(2)),
+                          (self.action_net, 0.01), (self.value_net, 1.0)):
+            for m in mod.modules() if isinstance(mod, nn.Sequential) else [mod]:
+                if isinstance(m, nn.Linear):
+                    nn.init.orthogonal_(m.weight, gain=gain)
+                    nn.init.zeros_(m.bias)
+
+    def forward(self, obs):
+        mean = self.action_net(self.mlp_extractor.policy_net(obs))
+        value = self.value_net(self.mlp_extractor.value_net(obs)).squeeze(-1)
+        return mean, value
+
+    @staticmethod
+    def log_prob(mean, log_std, actions):
+        var = torch.exp(2 * log_std)
+        return (-((actions - mean) ** 2) / (2 * var) - log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+
+    def act(self, obs, deterministic=False):
+        mean, value = self(obs)
+        if deterministic:
+            return mean, value, torch.zeros_like(value)
+        a = mean + torch.randn_like(mean) * torch.exp(self.log_std)
+        return a, value, self.log_prob(mean, self.log_std, a)
+
+    def evaluate(self, obs, actions):
+        mean, value = self(obs)
+        ent = (0.5 + 0.5 * math.log(2 * math.pi) + self.log_std).sum().expand(obs.shape[0])
+        return value, self.log_prob(mean, self.log_std, actions), ent
+
+
+def compute_gae(rewards, values, dones, last_values, gamma, lam):
+    """SB3 ``RolloutBuffer.compute_returns_and_advantage``.  rewards/values/dones: [T, N]; dones[t] = episode ended AT step t."""
+    T = rewards.shape[0]
+    adv = torch.zeros_like(rewards)
+    last = torch.zeros_like(last_values)
+    for t in reversed(range(T)):
+        next_v = last_values if t == T - 1 else values[t + 1]
+        nonterminal = 1.0 - dones[t]
+        delta = rewards[t] + gamma * next_v * nonterminal - values[t]
+        last = delta + gamma * lam * nonterminal * last
+        adv[t] = last
+    return adv, adv + values
+
+
+class PPO:
+    def __init__(self, env, n_steps=32, batch_size=None, n_epochs=10, learning_rate=3e-4, gamma=0.99, gae_lambda=0.95, clip_range=0.2,
+                 ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, net_arch=None, seed=0, normalize=True, verbose=0):
+        self.env = env  # BatchedUltrasound
+        self.device = env.device
+        self.N, self.obs_dim, self.act_dim = env.num_envs, env.obs.shape[1], env.action_dim
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.n_steps, self.n_epochs = n_steps, n_epochs
+        self.batch_size = batch_size or (64 if self.N * n_steps <= 64 * 2048 and self.N <= 64 else max(64, self.N * n_steps // 32))
+        self.lr, self.gamma, self.lam, self.clip, self.ent_coef, self.vf_coef, self.max_grad_norm = (
+            learning_rate, gamma, gae_lambda, clip_range, ent_coef, vf_coef, max_grad_norm)
+        arch = (net_arch or [dict(pi=[256, 128], vf=[256, 128])])[0]
+        torch.manual_seed(seed)  # same initial weights on every rank; sampling streams are then offset by rank
+        self.policy = MlpPolicy(self.obs_dim, self.act_dim, tuple(arch["pi"]), tuple(arch["vf"])).to(self.device)
+        if self.world > 1:
+            for p in self.policy.parameters():
+                dist.broadcast(p.data, 0)
+        torch.manual_seed(seed + 1000 * (self.rank + 1))
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5)
+        self.norm = VecNormalizeState(self.N, self.obs_dim, self.device, gamma=gamma) if normalize else None
+        lo, hi = env.action_spec
+        self.act_lo = torch.as_tensor(lo, dtype=torch.float32, device=self.device)
+        self.act_hi = torch.as_tensor(hi, dtype=torch.float32, device=self.device)
+        self.num_timesteps, self._n_updates, self.verbose = 0, 0, verbose
+        self.ep_ret = torch.zeros(self.N, dtype=torch.float64, device=self.device)
+        self.ep_len = torch.zeros(self.N, dtype=torch.float64, device=self.device)
+        self.last_stats: Dict[str, float] = {}
+        self._last_obs = None
+
+    # ------------------------------------------------------------------ rollouts
+    def _setup(self):
+        self._last_obs = self.env.reset().clone()
+        if self.norm is not None:
+            self.norm.obs_rms.update(self._last_obs, sync=True)
+
+    def collect_rollouts(self):
+        T, N, dev = self.n_steps, self.N, self.device
+        obs_b = torch.empty(T, N, self.obs_dim, device=dev)
+        raw_b = torch.empty(T, N, self.obs_dim, device=dev)
+        act_b = torch.empty(T, N, self.act_dim, device=dev)
+        rew_b, val_b, logp_b, done_b = (torch.empty(T, N, device=dev) for _ in range(4))
+        ret_trace = torch.empty(T, N, dtype=torch.float64, device=dev)
+        ep_r, ep_l, ep_n = (torch.zeros((), dtype=torch.float64, device=dev) for _ in range(3))
+        obs = self._last_obs
+        with torch.no_grad():
+            for t in range(T):
+                nobs = self.norm.normalize_obs(obs) if self.norm else obs
+                a, v, lp = self.policy.act(nobs)
+                raw_b[t], obs_b[t], act_b[t], val_b[t], logp_b[t] = obs, nobs, a, v, lp
+                o, r, d, _ = self.env.step(torch.max(torch.min(a, self.act_hi), self.act_lo), auto_reset=True)
+                d = d.to(torch.float32)
+                rew_b[t], done_b[t] = r, d
+                self.ep_ret += r.to(torch.float64)
+                self.ep_len += 1
+                if self.norm is not None:
+                    self.norm.returns = self.norm.returns * self.gamma + r.to(torch.float64)
+                    ret_trace[t] = self.norm.returns
+                    self.norm.returns = self.norm.returns * (1 - d.to(torch.float64))
+                dm = d.to(torch.float64)
+                ep_r += (self.ep_ret * dm).sum(); ep_l += (self.ep_len * dm).sum(); ep_n += dm.sum()
+                self.ep_ret *= 1 - dm
+                self.ep_len *= 1 - dm
+                obs = o.clone()
+            self._last_obs = obs
+            last_v = self.policy(self.norm.normalize_obs(obs) if self.norm else obs)[1]
+            if self.norm is not None:
+                # one merge of the rollout's moments (NCCL all-reduce when world > 1), then normalise the stored rewards
+                self.norm.ret_rms.update(ret_trace, sync=True)
+                rew_n = self.norm.normalize_reward(rew_b)
+                self.norm.obs_rms.update(raw_b, sync=True)
+            else:
+                rew_n = rew_b
+            adv, ret = compute_gae(rew_n, val_b, done_b, last_v, self.gamma, self.lam)
+        ep_r, ep_l, ep_n = allreduce_episode_stats(ep_r, ep_l, ep_n)
+        self.num_timesteps += T * N * self.world
+        self.last_stats.update(ep_rew_mean=float(ep_r / ep_n) if ep_n > 0 else float("nan"),
+                               ep_len_mean=float(ep_l / ep_n) if ep_n > 0 else float("nan"), episodes=float(ep_n),
+                               step_reward_mean=float(rew_b.mean()))
+        flat = lambda x: x.reshape(T * N, *x.shape[2:])
+        return flat(obs_b), flat(act_b), flat(val_b), flat(logp_b), flat(adv), flat(ret)
+
+    # ------------------------------------------------------------------ update
+    def _allreduce_grads(self):
+        if self.world == 1:
+            return
+        grads = [p.grad for p in self.policy.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])  # one flat bucket (~308 KB fp32), latency bound
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat /= self.world
+        off = 0
+        for g in grads:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
+
+    def train(self, batch):
+        obs, act, old_v, old_lp, adv, ret = batch
+        n = obs.shape[0]
+        pl = vl = kl = torch.zeros((), device=self.device)
+        for _ in range(self.n_epochs):
+            perm = torch.randperm(n, device=self.device)
+            for s in range(0, n - self.batch_size + 1, self.batch_size):
+                idx = perm[s:s + self.batch_size]
+                a = adv[idx]
+                a = (a - a.mean()) / (a.std() + 1e-8)
+                v, lp, ent = self.policy.evaluate(obs[idx], act[idx])
+                ratio = torch.exp(lp - old_lp[idx])
+                pl = -torch.min(a * ratio, a * torch.clamp(ratio, 1 - self.clip, 1 + self.clip)).mean()
+                vl = ((ret[idx] - v) ** 2).mean()
+                loss = pl + self.ent_coef * (-ent.mean()) + self.vf_coef * vl
+                self.opt.zero_grad(set_to_none=True)
+                loss.backward()
+                self._allreduce_grads()
+                nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
+                self.opt.step()
+                with torch.no_grad():
+                    kl = (old_lp[idx] - lp).mean()
+            self._n_updates += 1
+        self.last_stats.update(policy_loss=float(pl.detach()), value_loss=float(vl.detach()), approx_kl=float(kl), n_updates=self._n_updates)
+
+    def learn(self, total_timesteps: int, log_interval: int = 1, callback=None):
+        if self._last_obs is None:
+            self._setup()
+        it, t0 = 0, time.time()
+        while self.num_timesteps < total_timesteps:
+            self.train(self.collect_rollouts())
+            it += 1
+            if self.verbose and self.rank == 0 and it % log_interval == 0:
+                fps = self.num_timesteps / max(time.time() - t0, 1e-9)
+                print(f"[ppo] it {it} steps {self.num_timesteps} fps {fps:.0f} " + " ".join(f"{k} {v:.4g}" for k, v in self.last_stats.items()), flush=True)
+            if callback is not None:
+                callback(self)
+        return self
+
+    @torch.no_grad()
+    def predict(self, obs, deterministic=True):
+        nobs = self.norm.normalize_obs(obs) if self.norm else obs
+        a = self.policy.act(nobs, deterministic=deterministic)[0]
+        return torch.max(torch.min(a, self.act_hi), self.act_lo)
+
+    # ------------------------------------------------------------------ checkpoints (SB3 zip layout, SURVEY §5 [ART])
+    def save(self, path: str):
+        if self.rank != 0:
+            return
+        path = path if path.endswith(".zip") else path + ".zip"
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        data = {"num_timesteps": self.num_timesteps, "_n_updates": self._n_updates, "n_envs": self.N * self.world, "n_steps": self.n_steps,
+                "batch_size": self.batch_size, "n_epochs": self.n_epochs, "gamma": self.gamma, "gae_lambda": self.lam, "ent_coef": self.ent_coef,
+                "vf_coef": self.vf_coef, "max_grad_norm": self.max_grad_norm, "learning_rate": self.lr, "clip_range": self.clip,
+                "policy_class": "MlpPolicy", "net_arch": [dict(pi=[256, 128], vf=[256, 128])]}
+        with zipfile.ZipFile(path, "w") as z:
+            z.writestr("data", json.dumps(data))
+            for name, obj in (("policy.pth", self.policy.state_dict()), ("policy.optimizer.pth", self.opt.state_dict()), ("pytorch_variables.pth", {})):
+                buf = io.BytesIO()
+                torch.save(obj, buf)
+                z.writestr(name, buf.getvalue())
+            z.writestr("_stable_baselines3_version", SB3_VERSION)
+        if self.norm is not None:
+            with open(os.path.join(os.path.dirname(os.path.abspath(path)), "vec_normalize_" + os.path.basename(path)[:-4] + ".pkl"), "wb") as f:
+                pickle.dump(self.norm.state(), f)
+
+    def load(self, path: str, load_optimizer: bool = True):
+        path = path if path.endswith(".zip") else path + ".zip"
+        sd, data, opt = load_sb3_zip(path)
+        self.policy.load_state_dict({k: v.to(self.device) for k, v in sd.items()})
+        if load_optimizer and opt is not None:
+            try:
+                self.opt.load_state_dict(opt)
+            except Exception:
+                pass
+        self.num_timesteps, self._n_updates = int(data.get("num_timesteps", 0)), int(data.get("_n_updates", 0))
+        vn = os.path.join(os.path.dirname(os.path.abspath(path)), "vec_normalize_" + os.path.basename(path)[:-4] + ".pkl")
+        if self.norm is not None and os.path.exists(vn):
+            self.norm.load(load_vecnormalize(vn))
+        return self
+
+
+def load_sb3_zip(path: str):
+    """(policy state_dict, data dict, optimizer state or None) from an SB3-layout zip (the reference's trained_rl_models/*.zip)."""
+    with zipfile.ZipFile(path) as z:
+        data = json.loads(z.read("data"))
+        sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=False)
+        opt = None
+        if "policy.optimizer.pth" in z.namelist():
+            try:
+                opt = torch.load(io.BytesIO(z.read("policy.optimizer.pth")), map_location="cpu", weights_only=False)
+            except Exception:
+                opt = None
+    return sd, data, opt
+
+
+class _StubUnpickler(pickle.Unpickler):
+    """Reads SB3's VecNormalize pickle without SB3/gym installed (SURVEY App. D recipe)."""
+
+    def find_class(self, module, name):
+        if module.startswith("numpy") or module in ("collections", "builtins", "_codecs"):
+            return super().find_class(module, name)
+        return type(name, (), {"__setstate__": lambda self, st: self.__dict__.update(st if isinstance(st, dict) else {})})
+
+
+def load_vecnormalize(path: str) -> Dict[str, Any]:
+    """Normaliser statistics from our own pickle (plain dict) or from an SB3 ``VecNormalize.save`` pickle."""
+    with open(path, "rb") as f:
+        obj = _StubUnpickler(f).load()
+    if isinstance(obj, dict):
+        return obj
+    rms = lambda r: {"mean": np.asarray(r.mean), "var": np.asarray(r.var), "count": float(r.count)}
+    return {"obs_rms": rms(obj.obs_rms), "ret_rms": rms(obj.ret_rms), "gamma": float(obj.gamma), "clip_obs": float(obj.clip_obs),
+            "clip_reward": float(getattr(obj, "clip_reward", 10.0)), "epsilon": float(getattr(obj, "epsilon", 1e-8))}

@@ -402,6 +402,12 @@ def main():
         art[model] = entry
     with open(os.path.join(OUT, "art_stats.json"), "w") as f:
         json.dump(art, f)
+    # weights of the shipped `tracking` policy (76,941 fp32 parameters) + its normaliser: the closed-loop behavioural probe
+    import torch
+    z = zipfile.ZipFile(os.path.join(mdir, "tracking.zip"))
+    sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=False)
+    np.savez_compressed(os.path.join(OUT, "tracking_policy.npz"), **{k: v.numpy() for k, v in sd.items()},
+                        obs_mean=np.array(art["tracking"]["obs_mean"]), obs_var=np.array(art["tracking"]["obs_var"]))
     print("wrote art_stats.json:", {k: (v["num_timesteps"], len(v["ep_returns"])) for k, v in art.items()})
 
 
