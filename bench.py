@@ -34,6 +34,16 @@ ENV_OPTS = dict(controller_configs=RL_CONTROLLER, control_freq=500, horizon=1000
 SEED = 3  # rl_config.yaml:1
 
 
+def ncu_traffic(envs_per_gpu):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (scaled to this launch's env count)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    return t["dram_bytes_per_launch"] * envs_per_gpu / t["envs_per_launch"]
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -236,7 +246,7 @@ def run_cuda(args):
             "gpu_launches": int(launches),
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.traffic, "kernel": "solve_kernel", "kernel_ms": kernel_ms, "peak_source": which,
+                         "traffic": args.traffic if args.traffic is not None else ncu_traffic(per_gpu), "kernel": "solve_kernel", "kernel_ms": kernel_ms, "peak_source": which,
                          "note": "algorithmic bytes 7008 B/env-step (SURVEY 8d); the step is FP32-issue/latency bound, not HBM bound"},
         }
         if world == 1 and not args.no_cpu:

@@ -56,6 +56,7 @@ struct PartTables {
   const float* iw_dof;  // [npart] dof_invweight0 of the slider
   const float* iw_body; // [npart] body_invweight0 (translational)
   const int* nbr;     // [npart][6]
+  const int* nbrpk;   // [npart][6] packed (pair << 16) | neighbour; empty slots = (npair << 16) | self
 };
 
 __constant__ DevModel dm;  // single translation unit (usim.cu)

@@ -14,10 +14,24 @@
 #pragma once
 #include "common.cuh"
 
-#ifndef WARPS_PER_CTA
-#define WARPS_PER_CTA 1 // one env per CTA: no CTA waits for its slowest env (measured 1/2/4/8 warps: 2.17/2.12/1.96/1.82 M steps/s)
+// One env per CTA (no CTA waits for a slower env; measured 1/2/4/8 envs per CTA: 2.17/2.12/1.96/1.82 M steps/s).
+// WPE warps cooperate on that env over the same shared-memory image: more resident warps per SM without more shared memory.
+#ifndef WPE
+#define WPE 1
 #endif
+#define NT (32 * WPE)
+#define RED_MAX 24
 #define NPAIR_MAX 544
+// unroll factor of the hot per-slider / per-contact loops of the CG iteration: trades ILP against the size of the loop body
+// (the body must stay inside the instruction cache; `no_instruction` was the top stall of the first profile)
+// measured 4096 envs: compiler default 3.66 M steps/s, forced unroll 1 / 2 / 4: 3.20 / 2.74 / 2.64 M -> leave it to the compiler
+#define USIM_STR2(x) #x
+#define USIM_STR(x) USIM_STR2(x)
+#ifdef HOT_UNROLL
+#define PRAGMA_HOT _Pragma(USIM_STR(unroll HOT_UNROLL))
+#else
+#define PRAGMA_HOT
+#endif
 
 struct __align__(16) WS {
   float qs[NPART_MAX];                                 // slider position (slider velocity lives in hs[13..] until the CG loop starts)
@@ -34,11 +48,16 @@ struct __align__(16) WS {
   float R[9], p[3], vf[6], qdarm[7];
   float Mff[36], Sf[36], Pa[49];
   float mc[3], dv[12], red[24];
+  float red2[2][WPE][RED_MAX]; // double-buffered cross-warp reduction scratch
+  int cnt2[2][WPE];
   float lsign[7], lD[7], laref[7];
   float Dt, areft, mtot;
   int ncon;
 };
 
+__device__ __forceinline__ void env_sync() {
+  if (WPE == 1) __syncwarp(); else __syncthreads();
+}
 __device__ __forceinline__ float wsum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -95,18 +114,47 @@ __device__ __forceinline__ void seg_seg(v3 p1, v3 q1, v3 p2, v3 q2, v3& c1, v3& 
 }
 
 // mode: 0 = env step, 1 = reset forward (no integration; initialises the running statistics)
-__global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
+__global__ void __launch_bounds__(NT, 8) solve_kernel(
     int n, int mode, const uint8_t* __restrict__ mask, float* __restrict__ qpos, float* __restrict__ qvel, float* __restrict__ warm,
     float* __restrict__ task, const float* __restrict__ armbuf, PartTables pt, const int* __restrict__ eq_pairs,
     const short* __restrict__ nbr_pair, float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
     float* __restrict__ diag, int* __restrict__ ncon_out, int* __restrict__ geom1_out, int* __restrict__ geom2_out,
     float* __restrict__ dist_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int env = blockIdx.x * WARPS_PER_CTA + wid;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int env = blockIdx.x;
   if (env >= n) return;
   if (mask && !mask[env]) return;
-  WS& w = reinterpret_cast<WS*>(smem_raw)[wid];
+  WS& w = *reinterpret_cast<WS*>(smem_raw);
+  int rphase = 0;
+  // block-wide sums of K values: warp shuffles, then one barrier over double-buffered scratch (identical result in every thread)
+  auto bsumk = [&](auto& v) {
+    constexpr int K = sizeof(v) / sizeof(float);
+    static_assert(K <= RED_MAX, "reduction batch too large");
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = wsum(v[k]);
+    if (WPE > 1) {
+      float(*buf)[RED_MAX] = w.red2[rphase];
+      rphase ^= 1;
+      if (lane == 0) { // lane 0 of EVERY warp publishes its warp's partial sums
+#pragma unroll
+        for (int k = 0; k < K; k++) buf[wrp][k] = v[k];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < WPE; q++) t += buf[q][k];
+        v[k] = t;
+      }
+    }
+  };
+  auto bsum = [&](float x) -> float {
+    float v1[1] = {x};
+    bsumk(v1);
+    return v1[0];
+  };
   float* ts_g = task + (size_t)env * USIM_TASK_DIM;
   if (mode == 0 && ts_g[USIM_TS_DONE] != 0.f) return;
   const int np = dm.soft ? dm.npart : 0;
@@ -117,23 +165,23 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
   float* wm_g = warm + (size_t)env * QPAD;
 
   // ------------------------------------------------------------------ load
-  for (int i = lane; i < ARMBUF; i += 32) w.ab[i] = armbuf[(size_t)env * ARMBUF + i];
-  for (int i = lane; i < USIM_TASK_DIM; i += 32) w.ts[i] = ts_g[i];
-  for (int i = lane; i < QPAD; i += 32) { w.x[i] = i < nv ? wm_g[i] : 0.f; w.grad[i] = 0.f; }
-  for (int i = lane; i < np; i += 32) {
+  for (int i = tid; i < ARMBUF; i += NT) w.ab[i] = armbuf[(size_t)env * ARMBUF + i];
+  for (int i = tid; i < USIM_TASK_DIM; i += NT) w.ts[i] = ts_g[i];
+  for (int i = tid; i < QPAD; i += NT) { w.x[i] = i < nv ? wm_g[i] : 0.f; w.grad[i] = 0.f; }
+  for (int i = tid; i < np; i += NT) {
     w.qs[i] = qp_g[14 + i]; w.hs[13 + i] = qv_g[13 + i];
   }
-  if (lane < 7) w.qdarm[lane] = qv_g[lane];
+  if (tid < 7) w.qdarm[tid] = qv_g[tid];
   float quat[4] = {1, 0, 0, 0};
   if (dm.soft) {
-    if (lane < 6) w.vf[lane] = qv_g[7 + lane];
-    if (lane < 3) w.p[lane] = qp_g[7 + lane];
+    if (tid < 6) w.vf[tid] = qv_g[7 + tid];
+    if (tid < 3) w.p[tid] = qp_g[7 + tid];
     quat[0] = qp_g[10]; quat[1] = qp_g[11]; quat[2] = qp_g[12]; quat[3] = qp_g[13];
     float nq = rsqrtf(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3]);
     quat[0] *= nq; quat[1] *= nq; quat[2] *= nq; quat[3] *= nq;
-    if (lane == 0) quat2mat(quat, w.R);
+    if (tid == 0) quat2mat(quat, w.R);
   }
-  __syncwarp();
+  env_sync();
   const float off = dm.cap_r + dm.cap_hl;
   const v3 site = ld3(w.ab + AB_EEFPOS), ptip = ld3(w.ab + AB_PTIP), pback = ld3(w.ab + AB_PBACK);
   float R[9];
@@ -150,7 +198,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     v3 gl = mtv(R, ld3(dm.g));
     float a_mc[3] = {0, 0, 0}, a_I[6] = {0, 0, 0, 0, 0, 0}, a_F[3] = {0, 0, 0}, a_T[3] = {0, 0, 0}, a_q = 0.f, a_v = 0.f;
     const float m = dm.part_mass;
-    for (int i = lane; i < np; i += 32) {
+    for (int i = tid; i < np; i += NT) {
       v3 ah = ld3(pt.axis + 3 * i), r0 = ld3(pt.pos + 3 * i);
       float q = w.qs[i], sd = w.hs[13 + i];
       v3 c = r0 + (q - off) * ah;
@@ -172,18 +220,23 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       w.dg[i] = m + D;
       w.grad[13 + i] += D * (-B * sd - K * imp * q);
     }
+    {
+      float r17[17] = {a_mc[0], a_mc[1], a_mc[2], a_F[0], a_F[1], a_F[2], a_T[0], a_T[1], a_T[2],
+                       a_I[0], a_I[1], a_I[2], a_I[3], a_I[4], a_I[5], a_q, a_v};
+      bsumk(r17);
 #pragma unroll
-    for (int k = 0; k < 3; k++) { a_mc[k] = wsum(a_mc[k]); a_F[k] = wsum(a_F[k]); a_T[k] = wsum(a_T[k]); }
+      for (int k = 0; k < 3; k++) { a_mc[k] = r17[k]; a_F[k] = r17[3 + k]; a_T[k] = r17[6 + k]; }
 #pragma unroll
-    for (int k = 0; k < 6; k++) a_I[k] = wsum(a_I[k]);
-    a_q = wsum(a_q); a_v = wsum(a_v);
+      for (int k = 0; k < 6; k++) a_I[k] = r17[9 + k];
+      a_q = r17[15]; a_v = r17[16];
+    }
     // tendon equality: sum q = 0
     float K, B, imp;
     kbi(dm.solref[0], dm.solref[1], a_q, &K, &B, &imp);
     float Dt = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * dm.tendon_iw);
     float areft = -B * a_v - K * imp * a_q;
     float mtot = np * m + dm.center_mass;
-    if (lane == 0) {
+    if (tid == 0) {
       w.Dt = Dt; w.areft = areft; w.mtot = mtot;
       w.mc[0] = a_mc[0]; w.mc[1] = a_mc[1]; w.mc[2] = a_mc[2];
       // M_ff: [v (world); omega (body)]
@@ -207,22 +260,23 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       w.grad[7] = -bv.x - dm.free_damp * vlin.x; w.grad[8] = -bv.y - dm.free_damp * vlin.y; w.grad[9] = -bv.z - dm.free_damp * vlin.z;
       w.grad[10] = -bw.x - dm.free_damp * wl.x; w.grad[11] = -bw.y - dm.free_damp * wl.y; w.grad[12] = -bw.z - dm.free_damp * wl.z;
     }
-    __syncwarp();
+    env_sync();
     // "smooth" pair equalities (carry solrefsmooth = (-stiffness, -damping) of this episode)
-    for (int pr = lane; pr < dm.npair; pr += 32) {
+    for (int pr = tid; pr < dm.npair; pr += NT) {
       int a = eq_pairs[2 * pr], b = eq_pairs[2 * pr + 1];
       float pos = w.qs[a] - w.qs[b], vel = w.hs[13 + a] - w.hs[13 + b], K2, B2, imp2;
       kbi(ksm, bsm, pos, &K2, &B2, &imp2);
       float D = 1.f / fmaxf(1e-15f, (1.f - imp2) / imp2 * (pt.iw_dof[a] + pt.iw_dof[b]));
       w.Dp[pr] = D;
+      if (pr == 0) w.Dp[dm.npair] = 0.f; // the slot empty neighbour entries point at
       float ar = D * (-B2 * vel - K2 * imp2 * pos);
       atomicAdd(&w.grad[13 + a], ar); atomicAdd(&w.grad[13 + b], -ar);
       atomicAdd(&w.dg[a], D); atomicAdd(&w.dg[b], D);
     }
-    __syncwarp();
-    for (int i = lane; i < np; i += 32) { w.grad[13 + i] += w.Dt * w.areft; w.dg0[i] = w.dg[i] + w.Dt; }
+    env_sync();
+    for (int i = tid; i < np; i += NT) { w.grad[13 + i] += w.Dt * w.areft; w.dg0[i] = w.dg[i] + w.Dt; }
   }
-  if (lane < 7) {
+  if (tid < 7) {
     w.grad[lane] = w.ab[AB_QS + lane];
     // joint limits (margin 0)
     float q = qp_g[lane], lo = dm.jnt_lo[lane], hi = dm.jnt_hi[lane], dist = 0.f, sg = 0.f;
@@ -231,14 +285,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     kbi(dm.solref[0], dm.solref[1], dist, &K, &B, &imp);
     w.lsign[lane] = sg;
     w.lD[lane] = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * dm.iw_arm[lane]);
-    w.laref[lane] = -B * sg * w.qdarm[lane] - K * imp * dist;
+    w.laref[lane] = -B * sg * w.qdarm[tid] - K * imp * dist;
   }
-  __syncwarp();
+  env_sync();
 
   // ------------------------------------------------------------------ K4: collision, MuJoCo contact order
   int ncon = 0;
   { // (table, probe): geom1 = table, geom2 = probe
-    if (lane == 0) {
+    if (tid == 0) {
       v3 ends[2] = {ptip, pback};
       for (int e = 0; e < 2; e++) {
         float dist = ends[e].z - dm.probe_r - dm.table_z;
@@ -250,14 +304,16 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
         }
       }
     }
-    ncon = __shfl_sync(0xffffffffu, ncon, 0);
+    if (tid == 0) w.ncon = ncon;
+    env_sync();
+    ncon = w.ncon;
   }
   if (dm.soft) {
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) { // pass 0: (table, particle k); pass 1: (probe, particle k)
-      for (int base = 0; base < np; base += 32) {
-        int i = base + lane;
+      for (int base = 0; base < np; base += NT) {
+        int i = base + tid;
         bool h0 = false, h1 = false;
         v3 p0 = mk(0, 0, 0), p1 = mk(0, 0, 0), n0 = mk(0, 0, -1);
         float d0 = 0.f, d1 = 0.f;
@@ -284,7 +340,17 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
           }
         }
         unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
-        int slot = ncon + __popc(b0 & lt) + __popc(b1 & lt);
+        int before = 0, total = __popc(b0) + __popc(b1);
+        if (WPE > 1) { // cross-warp exclusive prefix of the per-warp hit counts (keeps the particle order)
+          int(*cb) = w.cnt2[rphase];
+          rphase ^= 1;
+          if (lane == 0) cb[wrp] = total;
+          __syncthreads();
+          total = 0;
+#pragma unroll
+          for (int q = 0; q < WPE; q++) { if (q < wrp) before += cb[q]; total += cb[q]; }
+        }
+        int slot = ncon + before + __popc(b0 & lt) + __popc(b1 & lt);
         if (h0 && slot < DEV_MAXC) {
           w.cpos[0][slot] = p0.x; w.cpos[1][slot] = p0.y; w.cpos[2][slot] = p0.z;
           w.cn[0][slot] = n0.x; w.cn[1][slot] = n0.y; w.cn[2][slot] = n0.z;
@@ -296,13 +362,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
           w.cn[0][slot] = 0.f; w.cn[1][slot] = 0.f; w.cn[2][slot] = -1.f;
           w.cdist[slot] = d1; w.cpart[slot] = (short)i; w.ctype[slot] = 0;
         }
-        ncon += __popc(b0) + __popc(b1);
+        ncon += total;
       }
     }
   }
   const int ncon_found = ncon;
   if (ncon > DEV_MAXC) ncon = DEV_MAXC;
-  __syncwarp();
+  env_sync();
 
   // ------------------------------------------------------------------ K5: contact parameters (aref, D)
   v3 Vs, Ws; // site velocity (linear, angular)
@@ -317,7 +383,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     }
     Vs = mk(s6[0], s6[1], s6[2]); Ws = mk(s6[3], s6[4], s6[5]);
   }
-  for (int c = lane; c < ncon; c += 32) {
+  for (int c = tid; c < ncon; c += NT) {
     int type = w.ctype[c], i = w.cpart[c];
     v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), t1, t2;
     make_frame(nn, &t1, &t2);
@@ -336,7 +402,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     w.cjv[1][c] = -B * dot(t1, rel);
     w.cjv[2][c] = -B * dot(t2, rel);
   }
-  __syncwarp();
+  env_sync();
 
   // ------------------------------------------------------------------ helpers (lambdas over the warp)
   // out = (M + E) in
@@ -345,31 +411,38 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     v3 ivl = mk(0, 0, 0);
     if (dm.soft) {
       ivl = mtv(R, ld3(in + 7)); // R^T in_v
-      for (int i = lane; i < np; i += 32) {
+      PRAGMA_HOT
+      for (int i = tid; i < np; i += NT) {
         float xi = in[13 + i];
         v3 ah = ld3(pt.axis + 3 * i);
         sx += xi;
         cl[0] += dm.part_mass * ah.x * xi; cl[1] += dm.part_mass * ah.y * xi; cl[2] += dm.part_mass * ah.z * xi;
       }
-      sx = wsum(sx); cl[0] = wsum(cl[0]); cl[1] = wsum(cl[1]); cl[2] = wsum(cl[2]);
-      for (int i = lane; i < np; i += 32) {
+      {
+        float r4[4] = {sx, cl[0], cl[1], cl[2]};
+        bsumk(r4);
+        sx = r4[0]; cl[0] = r4[1]; cl[1] = r4[2]; cl[2] = r4[3];
+      }
+      PRAGMA_HOT
+      for (int i = tid; i < np; i += NT) {
         float xi = in[13 + i];
         v3 ah = ld3(pt.axis + 3 * i);
         float acc = dm.part_mass * (dot(ah, ivl) + xi) + w.df[i] * xi + w.Dt * sx;
+        // 6 packed (pair << 16 | neighbour) entries, three 8-byte loads issued back to back, no data-dependent branch
+        const int2* row = reinterpret_cast<const int2*>(pt.nbrpk + 6 * i);
+        int2 e01 = row[0], e23 = row[1], e45 = row[2];
+        int ee[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-          int j = pt.nbr[6 * i + k];
-          if (j >= 0) acc += w.Dp[nbr_pair[6 * i + k]] * (xi - in[13 + j]);
-        }
+        for (int k = 0; k < 6; k++) acc += w.Dp[ee[k] >> 16] * (xi - in[13 + (ee[k] & 0xffff)]);
         out[13 + i] = acc;
       }
     }
-    if (lane < 7) {
+    if (tid < 7) {
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 7; j++) s += w.ab[AB_M + lane * 7 + j] * in[j];
       out[lane] = s;
-    } else if (lane < 13 && dm.soft) {
+    } else if (tid < 13 && dm.soft) {
       int r = lane - 7;
       float s = 0.f;
 #pragma unroll
@@ -377,27 +450,28 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       if (r < 3) s += R[3 * r] * cl[0] + R[3 * r + 1] * cl[1] + R[3 * r + 2] * cl[2];
       out[lane] = s;
     }
-    __syncwarp();
+    env_sync();
   };
   // dv[0..5] = Jsite in_arm ; dv[6..8] = in_v ; dv[9..11] = R in_omega
   auto dense_vel = [&](const float* in) {
-    if (lane < 6) {
+    if (tid < 6) {
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 7; j++) s += w.ab[AB_JSITE + lane * 7 + j] * in[j];
       w.dv[lane] = s;
-    } else if (lane < 9) {
+    } else if (tid < 9) {
       w.dv[lane] = dm.soft ? in[7 + lane - 6] : 0.f;
-    } else if (lane < 12) {
+    } else if (tid < 12) {
       int r = lane - 9;
       w.dv[lane] = dm.soft ? R[3 * r] * in[10] + R[3 * r + 1] * in[11] + R[3 * r + 2] * in[12] : 0.f;
     }
-    __syncwarp();
+    env_sync();
   };
   // out[j][c] = (J in)_c for the 3 rows of each contact (needs dense_vel(in) first)
   auto contactJ = [&](const float* in, float (*out)[DEV_MAXC], bool sub_aref) {
     v3 V = ld3(w.dv), W = ld3(w.dv + 3), iv = ld3(w.dv + 6), iw = ld3(w.dv + 9);
-    for (int c = lane; c < ncon; c += 32) {
+    PRAGMA_HOT
+    for (int c = tid; c < ncon; c += NT) {
       int type = w.ctype[c], i = w.cpart[c];
       v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), t1, t2;
       make_frame(nn, &t1, &t2);
@@ -408,15 +482,17 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       if (sub_aref) { o0 -= w.cjv[0][c]; o1 -= w.cjv[1][c]; o2 -= w.cjv[2][c]; }
       out[0][c] = o0; out[1][c] = o1; out[2][c] = o2;
     }
-    __syncwarp();
+    env_sync();
   };
   // grad = Hx - rhs - J^T f(jar); also returns probe wrench (force, torque about the site) via w.red[12..17]
   auto update_grad = [&]() -> bool {
-    for (int i = lane; i < QPAD; i += 32) w.grad[i] = i < nv ? w.Hx[i] : 0.f;
-    __syncwarp();
+    PRAGMA_HOT
+    for (int i = tid; i < QPAD; i += NT) w.grad[i] = i < nv ? w.Hx[i] : 0.f;
+    env_sync();
     bool changed = false;
     float g[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // particle-side (force, torque about P), probe-side (force, torque about site)
-    for (int c = lane; c < ncon; c += 32) {
+    PRAGMA_HOT
+    for (int c = tid; c < ncon; c += NT) {
       int type = w.ctype[c], i = w.cpart[c], zone;
       float fr, mu, f0, f1, f2, Dn = w.cD[c];
       contact_params(type, fr, mu);
@@ -437,9 +513,15 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
         g[6] += Fw.x; g[7] += Fw.y; g[8] += Fw.z; g[9] += T.x; g[10] += T.y; g[11] += T.z;
       }
     }
+    float g13[13];
 #pragma unroll
-    for (int k = 0; k < 12; k++) g[k] = wsum(g[k]);
-    if (lane < 7) {
+    for (int k = 0; k < 12; k++) g13[k] = g[k];
+    g13[12] = changed ? 1.f : 0.f;
+    bsumk(g13);
+#pragma unroll
+    for (int k = 0; k < 12; k++) g[k] = g13[k];
+    changed = g13[12] > 0.f;
+    if (tid < 7) {
       float s = 0.f;
 #pragma unroll
       for (int r = 0; r < 6; r++) s += w.ab[AB_JSITE + r * 7 + lane] * g[6 + r];
@@ -450,24 +532,25 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
         if (jar < 0.f) s += sg * (-w.lD[lane] * jar);
       }
       w.grad[lane] -= s;
-    } else if (lane < 10 && dm.soft) {
+    } else if (tid < 10 && dm.soft) {
       w.grad[lane] -= g[lane - 7];
-    } else if (lane < 13 && dm.soft) {
+    } else if (tid < 13 && dm.soft) {
       int r = lane - 10; // R^T torque
       w.grad[lane] -= R[r] * g[3] + R[3 + r] * g[4] + R[6 + r] * g[5];
     }
-    if (lane == 0) {
+    if (tid == 0) {
 #pragma unroll
       for (int k = 0; k < 6; k++) w.red[12 + k] = g[6 + k];
     }
-    __syncwarp();
-    return __any_sync(0xffffffffu, changed);
+    env_sync();
+    return changed;
   };
   // pg = P^-1 grad  (arm: dense 7x7 Cholesky; torso: arrow with the 6x6 Schur complement Sf)
   auto precond = [&]() {
     float t[6] = {0, 0, 0, 0, 0, 0};
     if (dm.soft) {
-      for (int i = lane; i < np; i += 32) {
+      PRAGMA_HOT
+      for (int i = tid; i < np; i += NT) {
         v3 ah = ld3(pt.axis + 3 * i), aw = mv(R, ah);
         v3 kk = mk(w.kx[i], w.ky[i], w.kz[i]);
         v3 bv = kk + dm.part_mass * aw;
@@ -476,14 +559,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
         float gi = w.grad[13 + i] / w.dg[i];
         t[0] += bv.x * gi; t[1] += bv.y * gi; t[2] += bv.z * gi; t[3] += bw.x * gi; t[4] += bw.y * gi; t[5] += bw.z * gi;
       }
-#pragma unroll
-      for (int k = 0; k < 6; k++) t[k] = wsum(t[k]);
+      bsumk(t);
       float y[6];
 #pragma unroll
       for (int k = 0; k < 6; k++) y[k] = w.grad[7 + k] - t[k];
       chol_solve<6>(w.Sf, y);
-      if (lane < 6) w.pg[7 + lane] = y[lane];
-      for (int i = lane; i < np; i += 32) {
+      if (tid < 6) w.pg[7 + lane] = y[lane];
+      PRAGMA_HOT
+      for (int i = tid; i < np; i += NT) {
         v3 ah = ld3(pt.axis + 3 * i), aw = mv(R, ah);
         v3 kk = mk(w.kx[i], w.ky[i], w.kz[i]);
         v3 bv = kk + dm.part_mass * aw;
@@ -498,34 +581,34 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
 #pragma unroll
       for (int j = 0; j < 7; j++) ya[j] = w.grad[j];
       chol_solve<7>(w.Pa, ya);
-      if (lane < 7) w.pg[lane] = ya[lane];
+      if (tid < 7) w.pg[lane] = ya[lane];
     }
-    __syncwarp();
+    env_sync();
   };
   auto vdot = [&](const float* a, const float* b) {
     float s = 0.f;
-#pragma unroll 1
-    for (int i = lane; i < nv; i += 32) s += a[i] * b[i];
-    return wsum(s);
+PRAGMA_HOT
+    for (int i = tid; i < nv; i += NT) s += a[i] * b[i];
+    return bsum(s);
   };
 
   // ------------------------------------------------------------------ K6: nonlinear PCG; pass -1 evaluates the warm start
-  for (int c = lane; c < ncon; c += 32) w.czone[c] = 255; // "unknown": the first update always reports a change
-  for (int i = lane; i < QPAD; i += 32) w.s[i] = 0.f;
-  __syncwarp();
+  for (int c = tid; c < ncon; c += NT) w.czone[c] = 255; // "unknown": the first update always reports a change
+  for (int i = tid; i < QPAD; i += NT) w.s[i] = 0.f;
+  env_sync();
 
   // preconditioner from the current active set (contact zones); rebuilt when the zones change
   auto build_precond = [&]() {
     // Runs 1-3 times per solve: written for SMALL CODE (rolled loops, stack arrays), not for speed, so that it does not
     // evict the CG loop body from the instruction cache.
 #pragma unroll 1
-    for (int i = lane; i < np; i += 32) { w.dg[i] = w.dg0[i]; w.kx[i] = 0.f; w.ky[i] = 0.f; w.kz[i] = 0.f; }
-    __syncwarp();
+    for (int i = tid; i < np; i += NT) { w.dg[i] = w.dg0[i]; w.kx[i] = 0.f; w.ky[i] = 0.f; w.kz[i] = 0.f; }
+    env_sync();
     float acc[42]; // packed upper triangles of the 6x6 wrench-space Hessians: [0..20] torso side (about P), [21..41] probe side (about the site)
 #pragma unroll
     for (int k = 0; k < 42; k++) acc[k] = 0.f;
 #pragma unroll 1
-    for (int c = lane; c < ncon; c += 32) {
+    for (int c = tid; c < ncon; c += NT) {
       int zone = w.czone[c], type = w.ctype[c], i = w.cpart[c];
       if (zone == 0) continue;
       float Dn = w.cD[c];
@@ -578,11 +661,15 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       if (type != 2) accum(acc, pos - P);
       if (type != 0) accum(acc + 21, pos - site);
     }
-#pragma unroll
-    for (int k = 0; k < 42; k++) acc[k] = wsum(acc[k]);
-    __syncwarp();
+    {
+      float(&lo21)[21] = *reinterpret_cast<float(*)[21]>(acc);
+      float(&hi21)[21] = *reinterpret_cast<float(*)[21]>(acc + 21);
+      bsumk(lo21);
+      bsumk(hi21);
+    }
+    env_sync();
     // arm block: Pa = M + Jsite^T Kp Jsite + limits   (lanes 0..6, column `lane`)
-    if (lane < 7) {
+    if (tid < 7) {
       float Kp6[36];
       {
         int idx = 21;
@@ -614,7 +701,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
 #pragma unroll
       for (int k = 0; k < 21; k++) sb[k] = 0.f;
 #pragma unroll 1
-      for (int i = lane; i < np; i += 32) {
+      for (int i = tid; i < np; i += NT) {
         v3 ah = ld3(pt.axis + 3 * i), aw = mv(R, ah);
         v3 kk = mk(w.kx[i], w.ky[i], w.kz[i]);
         v3 bv = kk + dm.part_mass * aw;
@@ -627,9 +714,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
 #pragma unroll
           for (int c2 = a2; c2 < 6; c2++) { sb[idx] += b6[a2] * b6[c2] * inv; idx++; }
       }
-#pragma unroll
-      for (int k = 0; k < 21; k++) sb[k] = wsum(sb[k]);
-      if (lane == 0) {
+      bsumk(sb);
+      if (tid == 0) {
         // rotate the angular part of Kf to the body frame: T = diag(I, R); Kl = T^T Kf T.  Scratch: hs[0..95] (dead here)
         float* Kf = w.hs; float* Kl = w.hs + 36; float* sbs = w.hs + 72;
         {
@@ -673,9 +759,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
         }
       }
     }
-    __syncwarp();
-    if (lane == 0) chol_rolled(w.Pa, 7);
-    __syncwarp();
+    env_sync();
+    if (tid == 0) chol_rolled(w.Pa, 7);
+    env_sync();
   };
 
   float gpg = 1.f, gnorm = 0.f, rhsn = 0.f;
@@ -697,30 +783,41 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     contactJ(vin, init ? w.cjar : w.cjv, init);
     if (init) {
       rhsn = sqrtf(vdot(w.grad, w.grad)); // grad holds rhs until here
-      for (int i = lane; i < nv; i += 32) w.Hx[i] -= w.grad[i];
-      __syncwarp();
+      PRAGMA_HOT
+      for (int i = tid; i < nv; i += NT) w.Hx[i] -= w.grad[i];
+      env_sync();
     } else {
       // ---- exact line search: Newton on phi'(alpha)
       float q1 = 0.f, q2 = 0.f;
-      for (int i = lane; i < nv; i += 32) { q1 += w.s[i] * w.Hx[i]; q2 += w.s[i] * w.hs[i]; }
-      q1 = wsum(q1); q2 = wsum(q2);
+      PRAGMA_HOT
+      for (int i = tid; i < nv; i += NT) { q1 += w.s[i] * w.Hx[i]; q2 += w.s[i] * w.hs[i]; }
+      {
+        float r2[2] = {q1, q2};
+        bsumk(r2);
+        q1 = r2[0]; q2 = r2[1];
+      }
       float alpha = 0.f, lo = 0.f, hi = -1.f, d0abs = 0.f;
 #pragma unroll 1
       for (int ls = 0; ls < 8; ls++) {
         float d1 = 0.f, d2 = 0.f;
-        for (int c = lane; c < ncon; c += 32) {
+        PRAGMA_HOT
+        for (int c = tid; c < ncon; c += NT) {
           float fr, mu, a1, a2, Dn = w.cD[c];
           contact_params(w.ctype[c], fr, mu);
           cone_ls(w.cjar[0][c] + alpha * w.cjv[0][c], w.cjar[1][c] + alpha * w.cjv[1][c], w.cjar[2][c] + alpha * w.cjv[2][c],
                   w.cjv[0][c], w.cjv[1][c], w.cjv[2][c], Dn, Dn * dm.impratio, mu, fr, a1, a2);
           d1 += a1; d2 += a2;
         }
-        if (lane < 7 && w.lsign[lane] != 0.f) {
+        if (tid < 7 && w.lsign[lane] != 0.f) {
           float sg = w.lsign[lane], jar = sg * (w.x[lane] + alpha * w.s[lane]) - w.laref[lane], jv = sg * w.s[lane];
           if (jar < 0.f) { d1 += w.lD[lane] * jar * jv; d2 += w.lD[lane] * jv * jv; }
         }
-        d1 = wsum(d1) + q1 + alpha * q2;
-        d2 = wsum(d2) + q2;
+        {
+          float r2[2] = {d1, d2};
+          bsumk(r2);
+          d1 = r2[0] + q1 + alpha * q2;
+          d2 = r2[1] + q2;
+        }
         if (ls == 0) d0abs = fabsf(d1);
         if (fabsf(d1) <= 1e-5f * d0abs || !(d2 > 0.f)) break;
         if (d1 < 0.f) lo = alpha; else hi = alpha;
@@ -730,11 +827,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
         if (an == alpha) break;
         alpha = an;
       }
-      for (int i = lane; i < nv; i += 32) { w.x[i] += alpha * w.s[i]; w.Hx[i] += alpha * w.hs[i]; }
-      for (int c = lane; c < ncon; c += 32) {
+      PRAGMA_HOT
+      for (int i = tid; i < nv; i += NT) { w.x[i] += alpha * w.s[i]; w.Hx[i] += alpha * w.hs[i]; }
+      PRAGMA_HOT
+      for (int c = tid; c < ncon; c += NT) {
         w.cjar[0][c] += alpha * w.cjv[0][c]; w.cjar[1][c] += alpha * w.cjv[1][c]; w.cjar[2][c] += alpha * w.cjv[2][c];
       }
-      __syncwarp();
+      env_sync();
     }
     bool changed = update_grad();
     float gpo = init ? 0.f : vdot(w.grad, w.pg); // with the previous pg (Polak-Ribiere)
@@ -750,8 +849,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     gnorm = sqrtf(vdot(w.grad, w.grad));
     float beta = restart ? 0.f : fmaxf(0.f, (gpn - gpo) / fmaxf(gpg, 1e-30f));
     gpg = gpn;
-    for (int i = lane; i < nv; i += 32) w.s[i] = -w.pg[i] + beta * w.s[i];
-    __syncwarp();
+    PRAGMA_HOT
+    for (int i = tid; i < nv; i += NT) w.s[i] = -w.pg[i] + beta * w.s[i];
+    env_sync();
   }
 
   // ------------------------------------------------------------------ K8: probe wrench, F/T torque
@@ -769,13 +869,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
     ft = mtv(w.ab + AB_EEFR, mk(t3[0], t3[1], t3[2]) - ctq);
   }
   bool in_contact = false;
-  for (int c = lane; c < ncon; c += 32) in_contact |= (w.ctype[c] == 1);
-  in_contact = __any_sync(0xffffffffu, in_contact);
+  for (int c = tid; c < ncon; c += NT) in_contact |= (w.ctype[c] == 1);
+  in_contact = bsum(in_contact ? 1.f : 0.f) > 0.f;
 
   // ------------------------------------------------------------------ K7: integrate (mj_Euler) and write the state back
   if (mode == 0) {
     // arm: implicit joint damping, (M + h D) qacc' = M qacc, through a dense 7x7 Cholesky on lane 0
-    if (lane == 0) {
+    if (tid == 0) {
       float A[49], b[7];
 #pragma unroll
       for (int r = 0; r < 7; r++) {
@@ -789,16 +889,16 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
 #pragma unroll
       for (int j = 0; j < 7; j++) w.qdarm[j] += h * b[j];
     }
-    __syncwarp();
-    for (int i = lane; i < nv; i += 32) wm_g[i] = w.x[i];
-    if (lane < 7) { qv_g[lane] = w.qdarm[lane]; qp_g[lane] += h * w.qdarm[lane]; }
+    env_sync();
+    for (int i = tid; i < nv; i += NT) wm_g[i] = w.x[i];
+    if (tid < 7) { qv_g[tid] = w.qdarm[tid]; qp_g[lane] += h * w.qdarm[tid]; }
     if (dm.soft) {
-      for (int i = lane; i < np; i += 32) {
+      for (int i = tid; i < np; i += NT) {
         float v = qv_g[13 + i] + h * w.x[13 + i];
         qv_g[13 + i] = v;
         qp_g[14 + i] = w.qs[i] + h * v;
       }
-      if (lane == 0) {
+      if (tid == 0) {
         v3 vn = vlin + h * ld3(w.x + 7), wn = wl + h * ld3(w.x + 10);
         st3(qv_g + 7, vn); st3(qv_g + 10, wn);
         st3(qp_g + 7, P + h * vn);
@@ -814,12 +914,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       }
     }
   }
-  __syncwarp();
+  env_sync();
 
   // ------------------------------------------------------------------ contact list / diagnostics
   if (ncon_out) {
-    if (lane == 0) ncon_out[env] = ncon;
-    for (int c = lane; c < ncon; c += 32) {
+    if (tid == 0) ncon_out[env] = ncon;
+    for (int c = tid; c < ncon; c += NT) {
       int type = w.ctype[c], g1, g2;
       if (type == 2) { g1 = 1; g2 = 2; } else { g1 = 4 + w.cpart[c]; g2 = type == 0 ? 1 : 2; }
       geom1_out[(size_t)env * DEV_MAXC + c] = g1;
@@ -829,7 +929,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
   }
 
   // ------------------------------------------------------------------ K9: task epilogue (lane 0)
-  if (lane == 0) {
+  if (tid == 0) {
     float* ts = w.ts;
     v3 hv = mk(0, 0, 0);
     {
@@ -906,6 +1006,6 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA) solve_kernel(
       d[23] = (float)(3 * ncon + nlim + (dm.soft ? 2 * 0 + np + dm.npair + 1 : 0));
     }
   }
-  __syncwarp();
-  for (int i = lane; i < USIM_TASK_DIM; i += 32) ts_g[i] = w.ts[i];
+  env_sync();
+  for (int i = tid; i < USIM_TASK_DIM; i += NT) ts_g[i] = w.ts[i];
 }

@@ -34,6 +34,7 @@ struct usim_handle {
   float *part_pos = nullptr, *part_axis = nullptr, *iw_dof = nullptr, *iw_body = nullptr;
   int *nbr = nullptr, *eq_pairs = nullptr;
   short* nbr_pair = nullptr;
+  int* nbrpk = nullptr;
   // staging for the host-buffer path
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_tobs = nullptr;
   uint8_t* h_done = nullptr;
@@ -187,6 +188,11 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   }
   CKH(upload(&h->part_pos, ppos)); CKH(upload(&h->part_axis, paxis)); CKH(upload(&h->iw_dof, iwd)); CKH(upload(&h->iw_body, iwb));
   CKH(upload(&h->nbr, nbr)); CKH(upload(&h->eq_pairs, pairs)); CKH(upload(&h->nbr_pair, nbrp));
+  {
+    std::vector<int> pk(nbr.size());
+    for (size_t e = 0; e < nbr.size(); e++) pk[e] = nbr[e] >= 0 ? ((int)nbrp[e] << 16) | nbr[e] : (d.npair << 16) | (int)(e / 6);
+    CKH(upload(&h->nbrpk, pk));
+  }
   CKH(cudaMallocHost((void**)&h->h_act, N * USIM_MAX_ACTION * sizeof(float)));
   CKH(cudaMallocHost((void**)&h->h_obs, N * USIM_OBS_DIM * sizeof(float)));
   CKH(cudaMallocHost((void**)&h->h_tobs, N * USIM_OBS_DIM * sizeof(float)));
@@ -200,7 +206,8 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   CKH(cudaMalloc((void**)&h->d_resetmask, N));
   CKH(cudaMemset(h->d_obs, 0, N * USIM_OBS_DIM * sizeof(float)));
   CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  h->smem = sizeof(WS) * WARPS_PER_CTA;
+  h->smem = sizeof(WS);
+  if (const char* pad = getenv("USIM_SMEM_PAD")) h->smem += (size_t)atoi(pad); // developer knob: trade resident CTAs for L1 capacity
   CKH(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   CKH(cudaDeviceSynchronize());
   *out = h;
@@ -214,7 +221,7 @@ int usim_destroy(usim_handle* h) {
   if (g_active == h) g_active = nullptr;
   for (auto& p : h->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   void* dev[] = {h->qpos, h->qvel, h->warm, h->task, h->armbuf, h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->part_pos,
-                 h->part_axis, h->iw_dof, h->iw_body, h->nbr, h->eq_pairs, h->nbr_pair, h->d_act, h->d_obs, h->d_tobs, h->d_rew,
+                 h->part_axis, h->iw_dof, h->iw_body, h->nbr, h->eq_pairs, h->nbr_pair, h->nbrpk, h->d_act, h->d_obs, h->d_tobs, h->d_rew,
                  h->d_done, h->d_resetmask};
   for (void* p : dev) if (p) cudaFree(p);
   void* host[] = {h->h_act, h->h_obs, h->h_tobs, h->h_rew, h->h_done};
@@ -224,7 +231,7 @@ int usim_destroy(usim_handle* h) {
   return 0;
 }
 
-static PartTables tables(const usim_handle* h) { return PartTables{h->part_pos, h->part_axis, h->iw_dof, h->iw_body, h->nbr}; }
+static PartTables tables(const usim_handle* h) { return PartTables{h->part_pos, h->part_axis, h->iw_dof, h->iw_body, h->nbr, h->nbrpk}; }
 
 // launches: the DevModel symbol is per-process; re-upload if another handle changed it
 static int activate(usim_handle* h) {
@@ -249,7 +256,7 @@ static int launch_forward(usim_handle* h, int mode, const uint8_t* mask, const f
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, s));
   }
-  solve_kernel<<<(n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, 32 * WARPS_PER_CTA, h->smem, s>>>(
+  solve_kernel<<<n, NT, h->smem, s>>>(
       n, mode, mask, h->qpos, h->qvel, h->warm, h->task, h->armbuf, tables(h), h->eq_pairs, h->nbr_pair, obs, rew, done, h->diag,
       h->ncon, h->geom1, h->geom2, h->cdist);
   if (timed) {
