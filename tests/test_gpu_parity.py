@@ -305,3 +305,44 @@ def test_create_rejects_bad_arguments():
         BatchedUltrasound(4, controller_configs=CC_TRACK, control_freq=20)  # 25 substeps: not built (rl_config uses 500 Hz)
     with pytest.raises(UsimError, match="num_envs"):
         BatchedUltrasound(0, controller_configs=CC_TRACK, control_freq=500)
+
+
+def test_contact_pair_indexing_is_exact_for_identical_states(O):
+    """north_star: bit-exact contact-pair indexing for identical states.  Both sides evaluate the SAME float32-representable
+    states (taken along an oracle trajectory); lists must be identical, pair by pair and in MuJoCo's order.  Only a pair whose
+    distance is below the fp32 evaluation error of the distance itself (1e-7 m) may differ."""
+    kw = dict(torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=5)
+    n = 4
+    env = _make(n, True, CC_TRACK, **kw)
+    env.reset()
+    orcs = [_oracle_from_gpu(O, env, True, CC_TRACK, i, **kw) for i in range(n)]
+    rng = np.random.default_rng(3)
+    checked = 0
+    for s in range(40):
+        a = rng.uniform(0, 1, size=(n, 6))
+        for i in range(n):
+            orcs[i].step(a[i])
+        if s % 4:
+            continue
+        st = [orcs[i].get_state() for i in range(n)]
+        q32 = np.array([x[0] for x in st], dtype=np.float32)
+        v32 = np.array([x[1] for x in st], dtype=np.float32)
+        w32 = np.array([x[2] for x in st], dtype=np.float32)
+        t32 = np.array([x[3] for x in st], dtype=np.float32)
+        env.set_state(q32, v32, w32, t32)
+        env.step(torch.as_tensor(a, dtype=torch.float32), auto_reset=False)  # the contact list belongs to the pre-step state
+        ncon, g1, g2, dist = env.contacts()
+        for i in range(n):
+            orcs[i].set_state(q32[i].astype(np.float64), v32[i].astype(np.float64), w32[i].astype(np.float64), t32[i].astype(np.float64))
+            orcs[i].forward(orcs[i].tau)
+            c = orcs[i].contacts()
+            k = int(ncon[i])
+            got = list(zip(g1[i, :k].tolist(), g2[i, :k].tolist()))
+            want = list(zip(c["geom1"].tolist(), c["geom2"].tolist()))
+            if got != want:
+                amb = {p for p, d in zip(want, c["dist"]) if abs(d) < 1e-7}
+                assert [p for p in got if p not in amb] == [p for p in want if p not in amb], (s, i)
+            np.testing.assert_allclose(dist[i, :k].cpu().numpy()[: len(want)] if got == want else [], c["dist"] if got == want else [], atol=2e-6)
+            checked += len(want)
+    assert checked > 1000
+    env.close()
