@@ -97,6 +97,8 @@ typedef struct usim_model {
   double timestep, gravity[3], impratio, solref[2], solimp[5], solref_smooth[2];
   double table_top_z, table_half_xy, table_friction, probe_friction, particle_friction;
   double init_qpos[7];
+  /* trajectory grid on the torso top (ultrasound.py:184-186,787-788,807): box 0.039/0.15/0.09, cylinder 0.041/0.15/0.05 */
+  double top_torso_offset, traj_x_range, traj_y_range;
 } usim_model;
 
 /* Env + controller options: the kwargs of `suite.make("Ultrasound", ...)`

@@ -1165,6 +1165,8 @@ void oracle_ik(oracle_env* e, const double* target, double* q7) {
   memcpy(e->qpos, save, sizeof save);
 }
 
+void oracle_grid_point2(double tx, double ty, double tz, double xr, double yr, double top, int ix, int iy, double* pt);
+
 void oracle_reset(oracle_env* e, double* obs) {
   const usim_model* m = e->m;
   const usim_config* c = &e->cfg;
@@ -1191,8 +1193,8 @@ void oracle_reset(oracle_env* e, double* obs) {
     memcpy(ts + USIM_TS_TRAJ_START, s, sizeof s); memcpy(ts + USIM_TS_TRAJ_END, en, sizeof en);
   } else {
     oracle_philox(c->seed, (uint32_t)e->gid, ep, 1, 0, r);
-    oracle_grid_point(tx, ty, tz, (int)(r[0] % 50u), (int)(r[1] % 50u), ts + USIM_TS_TRAJ_START);
-    oracle_grid_point(tx, ty, tz, (int)(r[2] % 50u), (int)(r[3] % 50u), ts + USIM_TS_TRAJ_END);
+    oracle_grid_point2(tx, ty, tz, m->traj_x_range, m->traj_y_range, m->top_torso_offset, (int)(r[0] % 50u), (int)(r[1] % 50u), ts + USIM_TS_TRAJ_START);
+    oracle_grid_point2(tx, ty, tz, m->traj_x_range, m->traj_y_range, m->top_torso_offset, (int)(r[2] % 50u), (int)(r[3] % 50u), ts + USIM_TS_TRAJ_END);
   }
   oracle_philox(c->seed, (uint32_t)e->gid, ep, 2, 0, r);
   ts[USIM_TS_U0] = u01(r[0]); /* ultrasound.py:443 (unseeded in the reference) */
@@ -1291,11 +1293,14 @@ void oracle_post_action(double* ts, int horizon, double control_freq, int early_
 }
 
 /* waypoint grid of get_trajectory (ultrasound.py:787-788,805-807): value of grid index i in [0,50) */
-void oracle_grid_point(double tx, double ty, double tz, int ix, int iy, double* pt) {
-  double x0 = -0.15 + tx + 0.03, x1 = 0.15 + tx, y0 = -0.09 + ty, y1 = 0.09 + ty;
+void oracle_grid_point2(double tx, double ty, double tz, double xr, double yr, double top, int ix, int iy, double* pt) {
+  double x0 = -xr + tx + 0.03, x1 = xr + tx, y0 = -yr + ty, y1 = yr + ty;
   pt[0] = x0 + (x1 - x0) * (double)ix / 49.0;
   pt[1] = y0 + (y1 - y0) * (double)iy / 49.0;
-  pt[2] = tz + 0.039;
+  pt[2] = tz + top;
+}
+void oracle_grid_point(double tx, double ty, double tz, int ix, int iy, double* pt) { /* box torso constants */
+  oracle_grid_point2(tx, ty, tz, 0.15, 0.09, 0.039, ix, iy, pt);
 }
 
 /* ------------------------------------------------------------------ state access / introspection */

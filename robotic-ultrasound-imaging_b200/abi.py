@@ -51,6 +51,7 @@ class UsimModel(C.Structure):
         ("table_top_z", C.c_double), ("table_half_xy", C.c_double), ("table_friction", C.c_double),
         ("probe_friction", C.c_double), ("particle_friction", C.c_double),
         ("init_qpos", C.c_double * 7),
+        ("top_torso_offset", C.c_double), ("traj_x_range", C.c_double), ("traj_y_range", C.c_double),
     ]
 
 
@@ -113,6 +114,7 @@ class PackedModel:
         s.table_top_z, s.table_half_xy, s.table_friction = p.table_top_z, p.table_half_xy, p.table_friction
         s.probe_friction, s.particle_friction = p.probe_friction, p.particle_friction
         s.init_qpos[:] = p.init_qpos
+        s.top_torso_offset, s.traj_x_range, s.traj_y_range = p.top_torso_offset, p.traj_x_range, p.traj_y_range
         self.struct = s
 
 

@@ -352,11 +352,11 @@ __global__ void __launch_bounds__(64) reset_kernel(int n, const uint8_t* __restr
     ts[0] = 0.062f; ts[1] = -0.020f; ts[2] = 0.896f; ts[3] = -0.032f; ts[4] = -0.075f; ts[5] = 0.896f;
   } else {          // :787-788, :805-807
     philox(dm.seed_lo, dm.seed_hi, gid, ep, 1, 0, r);
-    float x0 = -0.15f + tx + 0.03f, x1 = 0.15f + tx, y0 = -0.09f + ty, y1 = 0.09f + ty;
+    float x0 = -dm.traj_xr + tx + 0.03f, x1 = dm.traj_xr + tx, y0 = -dm.traj_yr + ty, y1 = dm.traj_yr + ty;
     for (int wv = 0; wv < 2; wv++) {
       ts[3 * wv + 0] = x0 + (x1 - x0) * (float)(r[2 * wv] % 50u) / 49.f;
       ts[3 * wv + 1] = y0 + (y1 - y0) * (float)(r[2 * wv + 1] % 50u) / 49.f;
-      ts[3 * wv + 2] = tz + 0.039f;
+      ts[3 * wv + 2] = tz + dm.top_offset;
     }
   }
   philox(dm.seed_lo, dm.seed_hi, gid, ep, 2, 0, r);

@@ -41,6 +41,7 @@ struct DevModel {
   int soft, npart, npair;
   float tendon_iw, free_damp, part_mass, center_mass;
   float torso_qpos0[7];
+  float top_offset, traj_xr, traj_yr; // trajectory grid on the torso top (ultrasound.py:184-186)
   float rot_I[6];          // constant rotational inertia (xx,yy,zz,xy,xz,yz): capsules about their COM + centre geom
   // config
   int mode, horizon, early_term, solref_rand, pos_rand, det_traj, uncouple, iters, adim, env_off, nq, nv, max_rebuilds;

@@ -106,6 +106,7 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   d.fr_probe_part = (float)fmax(m->probe_friction, m->particle_friction);
   d.probe_r = (float)m->probe_radius; d.cap_r = (float)m->cap_radius;
   d.iw_probe = (float)m->body_invweight0[2 * m->probe_body]; d.iw_table = 0.f;
+  d.top_offset = (float)m->top_torso_offset; d.traj_xr = (float)m->traj_x_range; d.traj_yr = (float)m->traj_y_range;
   d.soft = m->soft; d.npart = m->soft ? m->npart : 0; d.npair = m->soft ? m->npair : 0;
   std::vector<float> ppos, paxis, iwd, iwb;
   std::vector<int> nbr, pairs;

@@ -25,7 +25,7 @@ import torch
 
 from . import _lib
 from .abi import (DIAG_DIM, MAX_CONTACTS, OBS_DIM, TASK_DIM, PackedModel, action_bounds, action_dim, make_config)
-from .model import SceneParams, UltrasoundModel, build_model
+from .model import SceneParams, UltrasoundModel, build_model, cylinder_torso_params
 
 SENSOR_NAMES = (  # ultrasound.py:394-401, dims App. A.4
     ("eef_contact_force", 3),
@@ -279,11 +279,9 @@ class Ultrasound:
     ):
         assert gripper_types == "UltrasoundProbeGripper", "Tried to specify gripper other than UltrasoundProbeGripper in Ultrasound environment!"
         assert robots == "Panda", "Only the Panda arm is built in this round (UR5e: SURVEY §8f rank 2)"
-        assert use_box_torso, "Only the box torso is built in this round (cylinder torso: SURVEY §8f rank 2)"
         if use_camera_obs or has_renderer or has_offscreen_renderer:
             raise NotImplementedError("rendering / camera observations are out of scope of the hot path (SURVEY §2.1 #4, §8f rank 4)")
-        if save_data:
-            raise NotImplementedError("save_data CSV stream is a later row (SURVEY §8f rank 3)")
+        self.save_data = bool(save_data)
         self.use_camera_obs, self.use_object_obs = use_camera_obs, use_object_obs
         self.reward_scale, self.reward_shaping = reward_scale, reward_shaping
         self.horizon, self.control_freq = horizon, control_freq
@@ -294,7 +292,7 @@ class Ultrasound:
             1, device=device, soft_torso=soft_torso, controller_configs=controller_configs, control_freq=control_freq,
             horizon=horizon, early_termination=early_termination, torso_solref_randomization=torso_solref_randomization,
             initial_probe_pos_randomization=initial_probe_pos_randomization, deterministic_trajectory=deterministic_trajectory,
-            seed=seed)
+            seed=seed, scene_params=None if use_box_torso else cylinder_torso_params(soft_torso=soft_torso))
         self.robots = [_Robot(self)]
         self.timestep = 0
         self.done = True
@@ -319,6 +317,8 @@ class Ultrasound:
     def reset(self):
         flat = self.core.reset()[0].cpu().numpy().astype(np.float64)
         self.timestep, self.done = 0, False
+        if self.save_data:
+            self._init_data_collection()
         return self._obs_dict(flat)
 
     def step(self, action):
@@ -329,7 +329,68 @@ class Ultrasound:
         self.timestep += 1
         d = bool(done[0].item()) and not self.ignore_done
         self.done = d
-        return self._obs_dict(obs[0].cpu().numpy().astype(np.float64)), float(rew[0].item()), d, {}
+        flat = obs[0].cpu().numpy().astype(np.float64)
+        if self.save_data:
+            self._collect(np.asarray(action, dtype=np.float64).reshape(-1), flat, float(rew[0].item()), d)
+        return self._obs_dict(flat), float(rew[0].item()), d, {}
+
+    # -- save_data: the per-episode CSV stream of ultrasound.py:479-509 (allocation), :552-614 (collection), :890-910 (files)
+    _SIM_FILES = ("ee_pos", "ee_goal_pos", "ee_vel", "ee_goal_vel", "ee_running_mean_vel", "ee_quat", "ee_goal_quat", "ee_diff_quat",
+                  "ee_z_contact_force", "ee_z_goal_contact_force", "ee_z_running_mean_contact_force", "ee_z_derivative_contact_force",
+                  "ee_z_goal_derivative_contact_force", "is_contact", "q_pos", "q_torques", "time")
+    _REWARD_FILES = ("pos", "ori", "vel", "force", "derivative_force")
+
+    def _task_state(self):
+        return self.core.get_state()[3][0].cpu().numpy().astype(np.float64)
+
+    def _init_data_collection(self):
+        H, A = self.horizon, self.core.action_dim
+        dims = {"ee_pos": 3, "ee_goal_pos": 3, "ee_vel": 3, "ee_quat": 4, "ee_goal_quat": 4, "q_pos": 7, "q_torques": 7}
+        self._data = {k: np.zeros((H, dims[k])) if k in dims else np.zeros(H) for k in self._SIM_FILES}
+        self._data.update({"reward_" + k: np.zeros(H) for k in self._REWARD_FILES})
+        self._data["action"] = np.zeros((H, A))
+        self._prev_ts = self._task_state()  # reward() at step t uses the task state of step t-1 (ultrasound.py:525)
+
+    def _collect(self, action, flat, reward, done):
+        from .abi import GOAL_QUAT_XYZW, TS_DFZ, TS_FZ_MEAN, TS_IN_CONTACT, TS_ORI_ERR, TS_POS_ERR, TS_TRAJ_PT, TS_VEL_MEAN
+        ts, prev, dg = self._task_state(), self._prev_ts, self.core.diag()[0].cpu().numpy().astype(np.float64)
+        i, D = self.timestep - 1, self._data
+        D["ee_pos"][i], D["ee_goal_pos"][i], D["ee_vel"][i] = dg[6:9], ts[TS_TRAJ_PT:TS_TRAJ_PT + 3], flat[6:9]
+        D["ee_goal_vel"][i], D["ee_running_mean_vel"][i] = 0.04, ts[TS_VEL_MEAN]
+        D["ee_quat"][i], D["ee_goal_quat"][i], D["ee_diff_quat"][i] = dg[9:13], GOAL_QUAT_XYZW, ts[TS_ORI_ERR] / 0.2
+        D["ee_z_contact_force"][i], D["ee_z_goal_contact_force"][i] = flat[2], 5
+        D["ee_z_running_mean_contact_force"][i], D["ee_z_derivative_contact_force"][i] = ts[TS_FZ_MEAN], ts[TS_DFZ]
+        D["ee_z_goal_derivative_contact_force"][i], D["is_contact"][i] = 0, ts[TS_IN_CONTACT]
+        D["q_pos"][i], D["q_torques"][i] = self.robots[0]._joint_positions, dg[13:20]
+        D["time"][i] = (self.timestep - 1) / self.horizon * 100
+        c = ts[TS_IN_CONTACT] != 0
+        D["reward_pos"][i] = 5 * np.exp(-np.hypot(ts[TS_POS_ERR], ts[TS_POS_ERR + 1]))
+        D["reward_ori"][i] = np.exp(-ts[TS_ORI_ERR])
+        D["reward_vel"][i] = np.exp(-np.square(45 * (prev[TS_VEL_MEAN] - 0.04)))
+        D["reward_force"][i] = 3 * np.exp(-np.square(0.7 * (prev[TS_FZ_MEAN] - 5))) if c else 0
+        D["reward_derivative_force"][i] = 2 * np.exp(-np.square(0.01 * prev[TS_DFZ])) if c else 0
+        D["action"][i] = action
+        self._prev_ts = ts
+        if done:
+            for k in self._SIM_FILES:
+                self._save_data(D[k], "simulation_data", k)
+            for k in self._REWARD_FILES:
+                self._save_data(D["reward_" + k], "reward_data", k)
+            self._save_data(D["action"], "policy_data", "action")
+
+    @staticmethod
+    def _save_data(data, fldr, filename):
+        """ultrasound.py:890-910: first free `<filename>_<idx>.csv`, no header, no index."""
+        import os
+
+        import pandas as pd
+        os.makedirs(fldr, exist_ok=True)
+        idx = 1
+        path = os.path.join(fldr, filename + "_" + str(idx) + ".csv")
+        while os.path.exists(path):
+            idx += 1
+            path = os.path.join(fldr, filename + "_" + str(idx) + ".csv")
+        pd.DataFrame(data).to_csv(path, header=None, index=None)
 
     def _check_probe_contact_with_torso(self) -> bool:
         """ultrasound.py:714-736: any active contact between probe_collision and a geom named G\\d+_\\d+_\\d+."""
@@ -409,9 +470,10 @@ class UltrasoundVecEnv:
     def __init__(self, num_envs: int, env_options: Optional[Dict[str, Any]] = None, seed: int = 0, device=0, env_id_offset: int = 0):
         opts = dict(env_options or {})
         for k in ("env_id", "robots", "use_camera_obs", "use_object_obs", "has_renderer", "has_offscreen_renderer", "render_camera",
-                  "camera_names", "camera_heights", "camera_widths", "camera_depths", "reward_shaping", "save_data", "use_box_torso",
-                  "gripper_types"):
+                  "camera_names", "camera_heights", "camera_widths", "camera_depths", "reward_shaping", "save_data", "gripper_types"):
             opts.pop(k, None)
+        if not opts.pop("use_box_torso", True):
+            opts["scene_params"] = cylinder_torso_params()
         self.core = BatchedUltrasound(num_envs, device=device, seed=seed, env_id_offset=env_id_offset, **opts)
         self.num_envs = num_envs
         low, high = self.core.action_spec

@@ -197,7 +197,11 @@ class SceneParams:
     probe_tip_z: float = -0.05  # tip-sphere centre (tip surface at the grip_site origin)
     probe_back_z: float = -0.10
 
-    # ---- soft box composite (in tree)
+    # ---- soft composite (in tree): soft_box.xml (type box) or soft_human_torso.xml (type cylinder, `use_box_torso=False`)
+    comp_type: str = "box"
+    top_torso_offset: float = 0.039  # ultrasound.py:184 (0.041 for the cylinder)
+    traj_x_range: float = 0.15       # ultrasound.py:185
+    traj_y_range: float = 0.09       # ultrasound.py:186 (0.05 for the cylinder)
     comp_count: Tuple[int, int, int] = (9, 4, 11)
     comp_spacing: float = 0.035
     cap_radius: float = 0.0075
@@ -253,10 +257,14 @@ def _composite_box(p: SceneParams):
             for iz in range(cz):
                 if ix in (0, cx - 1) or iy in (0, cy - 1) or iz in (0, cz - 1):
                     index[(ix, iy, iz)] = len(pos)
-                    pos.append(
-                        p.comp_spacing
-                        * np.array([ix - 0.5 * (cx - 1), iy - 0.5 * (cy - 1), iz - 0.5 * (cz - 1)])
-                    )
+                    e = p.comp_spacing * np.array([ix - 0.5 * (cx - 1), iy - 0.5 * (cy - 1), iz - 0.5 * (cz - 1)])
+                    if p.comp_type == "cylinder":  # MuJoCo BoxProject [EXT-recall]: rescale (x, y) from the L-inf to the L2 ball
+                        l0, l2 = max(abs(e[0]), abs(e[1])), np.hypot(e[0], e[1])
+                        if l2 > 0:
+                            e[:2] *= l0 / l2
+                    elif p.comp_type != "box":
+                        raise ValueError(f"composite type {p.comp_type!r} not supported")
+                    pos.append(e)
                     names.append(f"G{ix}_{iy}_{iz}")
     pairs = []
     for (ix, iy, iz), a in index.items():
@@ -266,6 +274,11 @@ def _composite_box(p: SceneParams):
                 pairs.append((a, index[nb]))
     pairs.sort()
     return np.array(pos), names, np.array(pairs, dtype=np.int32)
+
+
+def cylinder_torso_params(**kw) -> SceneParams:
+    """`use_box_torso=False`: soft_human_torso.xml:8-14 (composite cylinder, bottom site at -0.05) and ultrasound.py:184-186."""
+    return SceneParams(comp_type="cylinder", top_torso_offset=0.041, traj_y_range=0.05, torso_pos=(0.0, 0.0, 0.8 + 0.005 + 0.05), **kw)
 
 
 def build_model(params: SceneParams | None = None) -> UltrasoundModel:

@@ -17,6 +17,7 @@ import yaml
 
 from .dist import shard_range
 from .env import BatchedUltrasound
+from .model import cylinder_torso_params
 from .ppo import PPO
 
 _ENV_KEYS = ("controller_configs", "control_freq", "horizon", "early_termination", "torso_solref_randomization",
@@ -28,9 +29,8 @@ def env_from_config(cfg: dict, num_envs: int, seed: int, device, env_id_offset: 
     assert rs.pop("env_id", "Ultrasound") == "Ultrasound" and rs.get("robots", "Panda") == "Panda"
     if rs.get("use_camera_obs") or rs.get("has_renderer") or rs.get("has_offscreen_renderer"):
         raise NotImplementedError("rendering is out of scope of the hot path")
-    if not rs.get("use_box_torso", True):
-        raise NotImplementedError("cylinder torso: later row (SURVEY §8f rank 2)")
-    return BatchedUltrasound(num_envs, device=device, seed=seed, env_id_offset=env_id_offset, **{k: rs[k] for k in _ENV_KEYS if k in rs})
+    extra = {} if rs.get("use_box_torso", True) else {"scene_params": cylinder_torso_params()}
+    return BatchedUltrasound(num_envs, device=device, seed=seed, env_id_offset=env_id_offset, **{k: rs[k] for k in _ENV_KEYS if k in rs}, **extra)
 
 
 def main(argv=None):

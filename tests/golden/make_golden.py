@@ -268,6 +268,10 @@ def main():
     env, names = make_env(Ultrasound)
     G["constants"] = {k: (jl(v) if isinstance(v, np.ndarray) else v) for k, v in vars(env).items()
                       if isinstance(v, (int, float, bool, np.ndarray)) and not k.startswith("_")}
+    env_c, _ = make_env(Ultrasound)
+    env_c.__init__(robots="Panda", controller_configs={"type": "OSC_POSE"}, control_freq=500, horizon=1000, use_camera_obs=False,
+                   use_object_obs=False, has_offscreen_renderer=False, use_box_torso=False)
+    G["constants_cylinder"] = {k: getattr(env_c, k) for k in ("top_torso_offset", "x_range", "y_range", "grid_pts", "use_box_torso")}
     rew = []
     for i in range(60):
         eef = np.array([0.0, 0.0, 0.9]) + rng.normal(scale=[0.02, 0.02, 0.01])

@@ -7,6 +7,8 @@ Stated tolerances (fp32 kernels vs float64 oracle, SURVEY §8d / BASELINE.md §4
   reward             5e-2 absolute
   contact pairs      exact (pairs whose oracle distance is within 1e-6 m of the threshold may differ)
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -345,4 +347,58 @@ def test_contact_pair_indexing_is_exact_for_identical_states(O):
             np.testing.assert_allclose(dist[i, :k].cpu().numpy()[: len(want)] if got == want else [], c["dist"] if got == want else [], atol=2e-6)
             checked += len(want)
     assert checked > 1000
+    env.close()
+
+
+def test_save_data_csv_stream(tmp_path, monkeypatch):
+    """ultrasound.py:479-509,552-614,890-910: same folders / file names / shapes; reward terms add up to the reward."""
+    import pandas as pd
+    from rui_b200.env import make
+    monkeypatch.chdir(tmp_path)
+    env = make("Ultrasound", robots="Panda", controller_configs=CC_TRACK, control_freq=500, horizon=6, save_data=True, seed=2)
+    for ep in range(2):
+        env.reset()
+        rewards = []
+        for s in range(6):
+            _, r, d, _ = env.step(np.full(6, 0.4))
+            rewards.append(r)
+        assert d
+    env.close()
+    sim = sorted(os.listdir(tmp_path / "simulation_data"))
+    assert len(sim) == 17 * 2 and "ee_pos_1.csv" in sim and "ee_pos_2.csv" in sim and "q_torques_2.csv" in sim
+    assert sorted(os.listdir(tmp_path / "reward_data")) == sorted(f"{k}_{i}.csv" for k in ("pos", "ori", "vel", "force", "derivative_force") for i in (1, 2))
+    assert sorted(os.listdir(tmp_path / "policy_data")) == ["action_1.csv", "action_2.csv"]
+    assert pd.read_csv(tmp_path / "simulation_data" / "ee_pos_2.csv", header=None).shape == (6, 3)
+    assert pd.read_csv(tmp_path / "simulation_data" / "q_pos_2.csv", header=None).shape == (6, 7)
+    assert pd.read_csv(tmp_path / "policy_data" / "action_2.csv", header=None).shape == (6, 6)
+    total = sum(pd.read_csv(tmp_path / "reward_data" / f"{k}_2.csv", header=None)[0].to_numpy() for k in ("pos", "ori", "vel", "force", "derivative_force"))
+    np.testing.assert_allclose(total, rewards, atol=2e-3)
+    t = pd.read_csv(tmp_path / "simulation_data" / "time_2.csv", header=None)[0].to_numpy()
+    np.testing.assert_allclose(t, np.arange(6) / 6 * 100)
+
+
+def test_cylinder_torso_parity(O):
+    """use_box_torso=False: the composite-cylinder torso through the same kernels, against the oracle."""
+    from rui_b200.abi import PackedModel
+    from rui_b200.env import BatchedUltrasound
+    from rui_b200.model import build_model, cylinder_torso_params
+    kw = dict(torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=3)
+    env = BatchedUltrasound(2, device=0, controller_configs=CC_TRACK, control_freq=500, scene_params=cylinder_torso_params(), **kw)
+    env.reset()
+    pk = PackedModel(build_model(cylinder_torso_params()))
+    e = O.OracleEnv(pk, abi.make_config(1, CC_TRACK, control_freq=500, **kw), 0)
+    e.reset()
+    q, v, w, t = [x[0].cpu().numpy().astype(np.float64) for x in env.get_state()]
+    np.testing.assert_allclose(t[:6], e.get_state()[3][:6], atol=2e-7)  # waypoints from the cylinder's grid (y range 0.05, top 0.041)
+    assert abs(t[2] - (0.855 + 0.041)) < 1e-6
+    e.set_state(q, v, w, t)
+    rng = np.random.default_rng(0)
+    for s in range(25):
+        a = rng.uniform(0, 1, size=(2, 6))
+        o, r, d, _ = env.step(torch.as_tensor(a, dtype=torch.float32), auto_reset=False)
+        oo, orr, od = e.step(a[0])
+        gq, gv = [x[0].cpu().numpy() for x in env.get_state()[:2]]
+        oq, ov = e.get_state()[:2]
+        assert np.abs(gq - oq).max() <= 1e-4 and np.abs(gv - ov).max() <= 2e-3
+        assert abs(float(o[0, 2]) - oo[2]) <= 1e-2 * abs(oo[2]) + 5e-2 and abs(float(r[0]) - orr) <= 5e-2
     env.close()

@@ -107,3 +107,18 @@ def test_reset_noise_and_draws(golden, O, soft_model):
     std = np.std(dev, axis=0)
     np.testing.assert_allclose(std, g["noise_std"], rtol=0.25)
     assert len(set(ks)) > 50 and len(set(bs)) > 15
+
+
+def test_cylinder_torso_constants(golden):
+    """use_box_torso=False (ultrasound.py:184-186, soft_human_torso.xml): trajectory-grid constants of the cylinder model."""
+    from rui_b200.model import build_model, cylinder_torso_params
+    c = golden["constants_cylinder"]
+    p = cylinder_torso_params()
+    assert c["use_box_torso"] is False
+    assert (p.top_torso_offset, p.traj_x_range, p.traj_y_range) == (c["top_torso_offset"], c["x_range"], c["y_range"]) == (0.041, 0.15, 0.05)
+    m = build_model(p)
+    assert (m.nq, m.nv, len(m.eq_pairs)) == (284, 283, 536)  # same topology as the box, projected geometry
+    pos = m.part_pos
+    assert np.hypot(pos[:, 0], pos[:, 1]).max() <= 0.14 + 1e-12  # (x, y) inside the L2 ball of the largest half extent
+    assert abs(np.abs(pos[:, 2]).max() - 0.175) < 1e-12
+    assert abs(p.torso_pos[2] - (0.8 + 0.005 + 0.05)) < 1e-12
