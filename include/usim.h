@@ -192,6 +192,9 @@ int usim_nv(const usim_handle* h);
 int usim_action_dim(const usim_handle* h);
 /* number of kernels launched by this handle so far (bench.py "gpu_launches") */
 int64_t usim_launch_count(const usim_handle* h);
+/* number of env steps whose constraint solve produced a non-finite result; such an env reports done = 1 with finite outputs
+ * and is wiped by the next reset (MuJoCo: "bad qacc" auto-reset).  Synchronises the device. */
+int usim_divergence_count(usim_handle* h, int64_t* count);
 /* elapsed device time (ms) of the dominant kernel over its launches since the
  * last call with reset != 0; measured with CUDA events on the launch stream */
 int usim_kernel_time(usim_handle* h, int reset, double* total_ms, int64_t* launches);

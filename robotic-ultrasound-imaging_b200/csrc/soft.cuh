@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     float* __restrict__ task, const float* __restrict__ armbuf, PartTables pt, const int* __restrict__ eq_pairs,
     const short* __restrict__ nbr_pair, float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
     float* __restrict__ diag, int* __restrict__ ncon_out, int* __restrict__ geom1_out, int* __restrict__ geom2_out,
-    float* __restrict__ dist_out) {
+    float* __restrict__ dist_out, int* __restrict__ diverged) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int env = blockIdx.x;
@@ -928,6 +928,8 @@ PRAGMA_HOT
     }
   }
 
+  // divergence guard (MuJoCo resets on bad qacc): a non-finite solution ends the episode, the reset wipes the state
+  const float xnorm2 = vdot(w.x, w.x);
   // ------------------------------------------------------------------ K9: task epilogue (lane 0)
   if (tid == 0) {
     float* ts = w.ts;
@@ -947,6 +949,13 @@ PRAGMA_HOT
     const float* quat_e = w.ab + AB_QUAT;
     float reward = 0.f;
     int dn = 0;
+    const bool bad = !isfinite(xnorm2) || !isfinite(cfrc.x + cfrc.y + cfrc.z) || !isfinite(ft.x + ft.y + ft.z) || !isfinite(hv.x + hv.y + hv.z) ||
+                     !isfinite(eef.x + eef.y + eef.z);
+    if (bad) { // keep the outputs finite; the episode ends below and the reset wipes the state
+      cfrc = mk(0, 0, 0); ft = mk(0, 0, 0); hv = mk(0, 0, 0);
+      if (!isfinite(eef.x + eef.y + eef.z)) eef = ld3(ts + USIM_TS_TRAJ_PT);
+      if (diverged) atomicAdd(diverged, 1);
+    }
     if (mode == 0) {
       ts[USIM_TS_TIMESTEP] += 1.f;
       if (in_contact) ts[USIM_TS_TOUCHED] = 1.f;
@@ -974,6 +983,7 @@ PRAGMA_HOT
         if (ts[USIM_TS_TOUCHED] != 0.f && !in_contact) term = 1;
         dn = dn || term;
       }
+      if (bad) dn = 1;
       ts[USIM_TS_DONE] = (float)dn;
     } else {
       ts[USIM_TS_FZ_PREV] = 0.f; ts[USIM_TS_DFZ] = 0.f;

@@ -30,6 +30,7 @@ struct usim_handle {
   float *qpos = nullptr, *qvel = nullptr, *warm = nullptr, *task = nullptr, *armbuf = nullptr, *diag = nullptr;
   int *ncon = nullptr, *geom1 = nullptr, *geom2 = nullptr;
   float* cdist = nullptr;
+  int* diverged = nullptr; // number of env steps that produced a non-finite solution (episode force-ended)
   // model tables
   float *part_pos = nullptr, *part_axis = nullptr, *iw_dof = nullptr, *iw_body = nullptr;
   int *nbr = nullptr, *eq_pairs = nullptr;
@@ -182,6 +183,8 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   CKH(cudaMemset(h->armbuf, 0, N * ARMBUF * sizeof(float)));
   CKH(cudaMemset(h->diag, 0, N * USIM_DIAG_DIM * sizeof(float)));
   CKH(cudaMemset(h->ncon, 0, N * sizeof(int)));
+  CKH(cudaMalloc((void**)&h->diverged, sizeof(int)));
+  CKH(cudaMemset(h->diverged, 0, sizeof(int)));
   { // task records: everything zero except DONE = 1 (must reset before stepping)
     std::vector<float> t(N * USIM_TASK_DIM, 0.f);
     for (size_t e = 0; e < N; e++) t[e * USIM_TASK_DIM + USIM_TS_DONE] = 1.f;
@@ -221,7 +224,7 @@ int usim_destroy(usim_handle* h) {
   cudaDeviceSynchronize();
   if (g_active == h) g_active = nullptr;
   for (auto& p : h->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-  void* dev[] = {h->qpos, h->qvel, h->warm, h->task, h->armbuf, h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->part_pos,
+  void* dev[] = {h->diverged, h->qpos, h->qvel, h->warm, h->task, h->armbuf, h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->part_pos,
                  h->part_axis, h->iw_dof, h->iw_body, h->nbr, h->eq_pairs, h->nbr_pair, h->nbrpk, h->d_act, h->d_obs, h->d_tobs, h->d_rew,
                  h->d_done, h->d_resetmask};
   for (void* p : dev) if (p) cudaFree(p);
@@ -259,7 +262,7 @@ static int launch_forward(usim_handle* h, int mode, const uint8_t* mask, const f
   }
   solve_kernel<<<n, NT, h->smem, s>>>(
       n, mode, mask, h->qpos, h->qvel, h->warm, h->task, h->armbuf, tables(h), h->eq_pairs, h->nbr_pair, obs, rew, done, h->diag,
-      h->ncon, h->geom1, h->geom2, h->cdist);
+      h->ncon, h->geom1, h->geom2, h->cdist, h->diverged);
   if (timed) {
     CK(cudaEventRecord(e1, s));
     h->pending.emplace_back(e0, e1);
@@ -384,6 +387,13 @@ int usim_nq(const usim_handle* h) { return h ? h->nq : -1; }
 int usim_nv(const usim_handle* h) { return h ? h->nv : -1; }
 int usim_action_dim(const usim_handle* h) { return h ? h->adim : -1; }
 int64_t usim_launch_count(const usim_handle* h) { return h ? h->launches : -1; }
+int usim_divergence_count(usim_handle* h, int64_t* count) {
+  if (!h || !count) return fail("usim_divergence_count: null argument");
+  int c = 0;
+  CK(cudaMemcpy(&c, h->diverged, sizeof(int), cudaMemcpyDeviceToHost)); // synchronises the device
+  *count = c;
+  return 0;
+}
 
 int usim_kernel_time(usim_handle* h, int reset, double* total_ms, int64_t* launches) {
   if (!h) return fail("usim_kernel_time: null handle");

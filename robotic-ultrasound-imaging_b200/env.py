@@ -201,6 +201,12 @@ class BatchedUltrasound:
     def launch_count(self) -> int:
         return int(_lib.lib().usim_launch_count(self._h))
 
+    @property
+    def divergence_count(self) -> int:
+        c = C.c_int64()
+        _lib.check(_lib.lib().usim_divergence_count(self._h, C.byref(c)))
+        return int(c.value)
+
     def kernel_time(self, reset: bool = True):
         ms, n = C.c_double(), C.c_int64()
         _lib.check(_lib.lib().usim_kernel_time(self._h, int(reset), C.byref(ms), C.byref(n)))

@@ -402,3 +402,22 @@ def test_cylinder_torso_parity(O):
         assert np.abs(gq - oq).max() <= 1e-4 and np.abs(gv - ov).max() <= 2e-3
         assert abs(float(o[0, 2]) - oo[2]) <= 1e-2 * abs(oo[2]) + 5e-2 and abs(float(r[0]) - orr) <= 5e-2
     env.close()
+
+
+def test_divergence_guard_ends_the_episode_with_finite_outputs():
+    """SURVEY §5 failure detection: a non-finite solve ends that env's episode, keeps outputs finite, and the reset wipes it."""
+    env = _make(16, True, CC_TRACK, seed=2)
+    env.reset()
+    q, v, w, t = env.get_state()
+    v[3, 20] = float("nan")   # poison one slider velocity of env 3
+    v[7, 2] = float("inf")    # and one arm joint velocity of env 7
+    env.set_state(q, v, w, t)
+    o, r, d, tobs = env.step(torch.full((16, 6), 0.5), auto_reset=True)
+    assert d.tolist() == [0, 0, 0, 1, 0, 0, 0, 1] + [0] * 8
+    assert torch.isfinite(o).all() and torch.isfinite(r).all() and torch.isfinite(tobs).all()
+    assert env.divergence_count == 2
+    for x in env.get_state():
+        assert torch.isfinite(x).all()  # the poisoned envs were re-initialised by the auto-reset
+    o, r, d, _ = env.step(torch.full((16, 6), 0.5), auto_reset=True)
+    assert not bool(d.any()) and env.divergence_count == 2 and torch.isfinite(o).all()
+    env.close()
