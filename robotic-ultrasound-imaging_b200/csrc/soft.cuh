@@ -11,58 +11,82 @@
 // Unknown vector layout (nv = 283): [0..6] arm, [7..9] free translation (world), [10..12] free
 // rotation (body frame), [13+i] slider i.  No constraint Jacobian is ever materialised: contact
 // rows are evaluated as rigid-body point velocities / wrenches, equality rows as a graph stencil.
+//
+// Structure of one CG iteration (every dot product rides on a pass that exists anyway; 5 warp reductions):
+//   applyH(s) [+ s.Hx, s.Hs]  ->  contact rows J s  ->  line search (Newton on phi')  ->  x, Hx, grad, jar updates [+ |Hx|^2]
+//   ->  contact forces into grad [+ probe wrench, zone changes]  ->  (preconditioner rebuild if the active set moved)
+//   ->  pg = P^-1 grad [+ grad.pg_old, grad.pg, |grad|^2, the slider sums of pg that the next applyH needs]  ->  s = -pg + beta s
 #pragma once
 #include "common.cuh"
 
-// One env per CTA (no CTA waits for a slower env; measured 1/2/4/8 envs per CTA: 2.17/2.12/1.96/1.82 M steps/s).
-// WPE warps cooperate on that env over the same shared-memory image: more resident warps per SM without more shared memory.
-#ifndef WPE
-#define WPE 1
-#endif
-#define NT (32 * WPE)
-#define RED_MAX 24
+// One env per CTA of one warp: no CTA waits for a slower env (measured 1/2/4/8 envs per CTA: 2.17/2.12/1.96/1.82 M steps/s).
+#define NT 32
 #define NPAIR_MAX 544
-// unroll factor of the hot per-slider / per-contact loops of the CG iteration: trades ILP against the size of the loop body
-// (the body must stay inside the instruction cache; `no_instruction` was the top stall of the first profile)
-// measured 4096 envs: compiler default 3.66 M steps/s, forced unroll 1 / 2 / 4: 3.20 / 2.74 / 2.64 M -> leave it to the compiler
-#define USIM_STR2(x) #x
-#define USIM_STR(x) USIM_STR2(x)
-#ifdef HOT_UNROLL
-#define PRAGMA_HOT _Pragma(USIM_STR(unroll HOT_UNROLL))
-#else
-#define PRAGMA_HOT
-#endif
 
 struct __align__(16) WS {
   float qs[NPART_MAX];                                 // slider position (slider velocity lives in hs[13..] until the CG loop starts)
   // Hx holds (M+E)x - rhs; during set-up `grad` accumulates rhs (= qfrc_smooth + J_eq^T D aref)
   float x[QPAD], Hx[QPAD], grad[QPAD], pg[QPAD], s[QPAD], hs[QPAD];
-  float dg[NPART_MAX], dg0[NPART_MAX], kx[NPART_MAX], ky[NPART_MAX], kz[NPART_MAX], df[NPART_MAX]; // dg0: diagonal without contacts
+  float dg[NPART_MAX], dgm[NPART_MAX];                 // dg: slider diagonal of the preconditioner, stored INVERTED; dgm: M+E diagonal w/o tendon
   float Dp[NPAIR_MAX];                                 // D of each "smooth" pair
   float cpos[3][DEV_MAXC], cn[3][DEV_MAXC], cjar[3][DEV_MAXC], cjv[3][DEV_MAXC]; // cjv holds aref until the first J*x
   float cD[DEV_MAXC], cdist[DEV_MAXC];
+  float sk[3][DEV_MAXC], sc[3][DEV_MAXC];              // per owner slot of a slider with contacts: K a (world), lever x K a
+  short cslot[NPART_MAX];                              // first contact slot of a slider (its "owner slot"), -1 = no contact
   short cpart[DEV_MAXC];
   unsigned char ctype[DEV_MAXC], czone[DEV_MAXC];
   float ab[ARMBUF];
   float ts[USIM_TASK_DIM];
   float R[9], p[3], vf[6], qdarm[7];
-  float Mff[36], Sf[36], Pa[49];
-  float mc[3], dv[12], red[24];
-  float red2[2][WPE][RED_MAX]; // double-buffered cross-warp reduction scratch
-  int cnt2[2][WPE];
+  float Mff[36], Mfw[21], Sf[49], Pa[49], Kp[21];      // Mfw: free-body inertia, world-frame omega, packed upper triangle; Sf/Pa: 7x7 Cholesky factors
+  float dv[12];
+  float r3[24], rg[16], rp[16], rq[8], rl[4];          // landing zones of the warp reductions (one per call site)
   float lsign[7], lD[7], laref[7];
-  float Dt, areft, mtot;
-  int ncon;
+  float Dt, areft;
+  int ncon, bad;
 };
 
-__device__ __forceinline__ void env_sync() {
-  if (WPE == 1) __syncwarp(); else __syncthreads();
-}
+__device__ __forceinline__ void env_sync() { __syncwarp(); }
 __device__ __forceinline__ float wsum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Transposing warp reduction of K values: K-1 shuffles instead of 5K.  Returns, in lane l, the warp total of entry
+// l & (KP-1), KP = K rounded up to a power of two.  Fixed association order -> bit-reproducible.
+template <int K>
+__device__ __forceinline__ float tsum(const float (&v)[K], int lane) {
+  constexpr int KP = K <= 1 ? 1 : K <= 2 ? 2 : K <= 4 ? 4 : K <= 8 ? 8 : K <= 16 ? 16 : 32;
+  static_assert(K <= 32, "tsum: at most 32 values");
+  float t[KP];
+#pragma unroll
+  for (int k = 0; k < KP; k++) t[k] = k < K ? v[k] : 0.f;
+#pragma unroll
+  for (int n = KP; n > 1; n >>= 1) {
+    const int o = n >> 1;
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; j++) {
+      float a = t[j], b = t[j + o];
+      float send = up ? a : b, keep = up ? b : a;
+      t[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+#pragma unroll
+  for (int o = KP; o < 32; o <<= 1) t[0] += __shfl_xor_sync(0xffffffffu, t[0], o);
+  return t[0];
+}
+// reduce K values and land them in shared memory (dst[0..K-1]); the caller syncs before reading
+template <int K>
+__device__ __forceinline__ void tsum_to(const float (&v)[K], int lane, float* dst) {
+  float r = tsum(v, lane);
+  if (lane < K) dst[lane] = r;
+}
+
+// (row, col) of entry l of a packed upper triangle of a 6x6, row-major
+__constant__ unsigned char c_tri6[21] = {0x00, 0x01, 0x02, 0x03, 0x04, 0x05, 0x11, 0x12, 0x13, 0x14, 0x15,
+                                         0x22, 0x23, 0x24, 0x25, 0x33, 0x34, 0x35, 0x44, 0x45, 0x55};
+__device__ __forceinline__ constexpr int tri6(int a, int b) { return a <= b ? a * 6 - a * (a - 1) / 2 + (b - a) : b * 6 - b * (b - 1) / 2 + (a - b); }
 
 __device__ __forceinline__ void cone_force(float j0, float j1, float j2, float Dn, float Dt, float mu, float fr, float& f0, float& f1,
                                            float& f2, int& zone) {
@@ -113,6 +137,56 @@ __device__ __forceinline__ void seg_seg(v3 p1, v3 q1, v3 p2, v3 q2, v3& c1, v3& 
   c2 = p2 + t * d2;
 }
 
+// In-place Cholesky of a 7x7 (row-major, both triangles valid on entry) held in shared memory, done in registers by ONE thread.
+// The factor is left in the lower triangle with its diagonal INVERTED (the solves multiply).
+__device__ __forceinline__ bool chol7_inv(float* A) {
+  float L[28];
+#pragma unroll
+  for (int i = 0; i < 7; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) L[i * (i + 1) / 2 + j] = A[i * 7 + j];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 7; j++) {
+    float s = L[j * (j + 1) / 2 + j];
+#pragma unroll
+    for (int k = 0; k < j; k++) s -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+    if (!(s > 0.f)) { ok = false; s = 1e-20f; }
+    float inv = rsqrtf(s);
+    L[j * (j + 1) / 2 + j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < 7; i++) {
+      float t = L[i * (i + 1) / 2 + j];
+#pragma unroll
+      for (int k = 0; k < j; k++) t -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+      L[i * (i + 1) / 2 + j] = t * inv;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 7; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) A[i * 7 + j] = L[i * (i + 1) / 2 + j];
+  return ok;
+}
+// x <- (L L^T)^-1 x for the leading N x N block of a factor written by chol7_inv (row pitch 7)
+template <int N>
+__device__ __forceinline__ void chol7_solve(const float* L, float* x) {
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    float t = x[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) t -= L[i * 7 + k] * x[k];
+    x[i] = t * L[i * 7 + i];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) {
+    float t = x[i];
+#pragma unroll
+    for (int k = i + 1; k < N; k++) t -= L[k * 7 + i] * x[k];
+    x[i] = t * L[i * 7 + i];
+  }
+}
+
 // mode: 0 = env step, 1 = reset forward (no integration; initialises the running statistics)
 __global__ void __launch_bounds__(NT, 8) solve_kernel(
     int n, int mode, const uint8_t* __restrict__ mask, float* __restrict__ qpos, float* __restrict__ qvel, float* __restrict__ warm,
@@ -121,40 +195,11 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     float* __restrict__ diag, int* __restrict__ ncon_out, int* __restrict__ geom1_out, int* __restrict__ geom2_out,
     float* __restrict__ dist_out, int* __restrict__ diverged) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid;
   const int env = blockIdx.x;
   if (env >= n) return;
   if (mask && !mask[env]) return;
   WS& w = *reinterpret_cast<WS*>(smem_raw);
-  int rphase = 0;
-  // block-wide sums of K values: warp shuffles, then one barrier over double-buffered scratch (identical result in every thread)
-  auto bsumk = [&](auto& v) {
-    constexpr int K = sizeof(v) / sizeof(float);
-    static_assert(K <= RED_MAX, "reduction batch too large");
-#pragma unroll
-    for (int k = 0; k < K; k++) v[k] = wsum(v[k]);
-    if (WPE > 1) {
-      float(*buf)[RED_MAX] = w.red2[rphase];
-      rphase ^= 1;
-      if (lane == 0) { // lane 0 of EVERY warp publishes its warp's partial sums
-#pragma unroll
-        for (int k = 0; k < K; k++) buf[wrp][k] = v[k];
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        float t = 0.f;
-#pragma unroll
-        for (int q = 0; q < WPE; q++) t += buf[q][k];
-        v[k] = t;
-      }
-    }
-  };
-  auto bsum = [&](float x) -> float {
-    float v1[1] = {x};
-    bsumk(v1);
-    return v1[0];
-  };
   float* ts_g = task + (size_t)env * USIM_TASK_DIM;
   if (mode == 0 && ts_g[USIM_TS_DONE] != 0.f) return;
   const int np = dm.soft ? dm.npart : 0;
@@ -167,11 +212,13 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
   // ------------------------------------------------------------------ load
   for (int i = tid; i < ARMBUF; i += NT) w.ab[i] = armbuf[(size_t)env * ARMBUF + i];
   for (int i = tid; i < USIM_TASK_DIM; i += NT) w.ts[i] = ts_g[i];
-  for (int i = tid; i < QPAD; i += NT) { w.x[i] = i < nv ? wm_g[i] : 0.f; w.grad[i] = 0.f; }
+  for (int i = tid; i < QPAD; i += NT) { w.x[i] = i < nv ? wm_g[i] : 0.f; w.grad[i] = 0.f; w.pg[i] = 0.f; w.s[i] = 0.f; }
   for (int i = tid; i < np; i += NT) {
-    w.qs[i] = qp_g[14 + i]; w.hs[13 + i] = qv_g[13 + i];
+    w.qs[i] = qp_g[14 + i]; w.hs[13 + i] = qv_g[13 + i]; w.cslot[i] = -1;
   }
+  for (int i = tid; i < 49; i += NT) w.Sf[i] = (i % 8 == 0) ? 1.f : 0.f; // identity: row/col 6 of the padded 6x6 stay like this
   if (tid < 7) w.qdarm[tid] = qv_g[tid];
+  if (tid == 0) w.bad = 0;
   float quat[4] = {1, 0, 0, 0};
   if (dm.soft) {
     if (tid < 6) w.vf[tid] = qv_g[7 + tid];
@@ -191,69 +238,80 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     for (int i = 0; i < 9; i++) R[i] = w.R[i];
     P = ld3(w.p); vlin = ld3(w.vf); wl = ld3(w.vf + 3); ww = mv(R, wl);
   }
+  const float mp = dm.part_mass;
+  // slider sums of the current search direction (or of x for the warm-start pass): sum_i v_i and m sum_i a_i v_i (torso frame)
+  float S4[4] = {0.f, 0.f, 0.f, 0.f};
 
   // ------------------------------------------------------------------ K3: torso inertia + bias, equality parameters
   const float ksm = -w.ts[USIM_TS_STIFFNESS], bsm = -w.ts[USIM_TS_DAMPING];
   if (dm.soft) {
     v3 gl = mtv(R, ld3(dm.g));
-    float a_mc[3] = {0, 0, 0}, a_I[6] = {0, 0, 0, 0, 0, 0}, a_F[3] = {0, 0, 0}, a_T[3] = {0, 0, 0}, a_q = 0.f, a_v = 0.f;
-    const float m = dm.part_mass;
+    // [0..2] m c, [3..5] F, [6..8] T, [9..14] parallel-axis inertia, [15] sum q, [16] sum qdot, [17] sum x, [18..20] m sum a x
+    float a[21];
+#pragma unroll
+    for (int k = 0; k < 21; k++) a[k] = 0.f;
     for (int i = tid; i < np; i += NT) {
       v3 ah = ld3(pt.axis + 3 * i), r0 = ld3(pt.pos + 3 * i);
-      float q = w.qs[i], sd = w.hs[13 + i];
+      float q = w.qs[i], sd = w.hs[13 + i], xi = w.x[13 + i];
       v3 c = r0 + (q - off) * ah;
-      a_mc[0] += m * c.x; a_mc[1] += m * c.y; a_mc[2] += m * c.z;
+      a[0] += mp * c.x; a[1] += mp * c.y; a[2] += mp * c.z;
       float cc = dot(c, c);
-      a_I[0] += m * (cc - c.x * c.x); a_I[1] += m * (cc - c.y * c.y); a_I[2] += m * (cc - c.z * c.z);
-      a_I[3] -= m * c.x * c.y; a_I[4] -= m * c.x * c.z; a_I[5] -= m * c.y * c.z;
+      a[9] += mp * (cc - c.x * c.x); a[10] += mp * (cc - c.y * c.y); a[11] += mp * (cc - c.z * c.z);
+      a[12] -= mp * c.x * c.y; a[13] -= mp * c.x * c.z; a[14] -= mp * c.y * c.z;
       v3 avp = cross(wl, cross(wl, c)) + 2.f * sd * cross(wl, ah);
-      v3 F = m * (avp - gl);
+      v3 F = mp * (avp - gl);
       v3 T = cross(c, F);
-      a_F[0] += F.x; a_F[1] += F.y; a_F[2] += F.z; a_T[0] += T.x; a_T[1] += T.y; a_T[2] += T.z;
-      a_q += q; a_v += sd;
-      w.grad[13 + i] = -dot(ah, F);
+      a[3] += F.x; a[4] += F.y; a[5] += F.z; a[6] += T.x; a[7] += T.y; a[8] += T.z;
+      a[15] += q; a[16] += sd;
+      a[17] += xi; a[18] += mp * ah.x * xi; a[19] += mp * ah.y * xi; a[20] += mp * ah.z * xi;
       // "fix" equality of this slider
       float K, B, imp;
       kbi(dm.solref[0], dm.solref[1], q, &K, &B, &imp);
       float D = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * pt.iw_dof[i]);
-      w.df[i] = D;
-      w.dg[i] = m + D;
-      w.grad[13 + i] += D * (-B * sd - K * imp * q);
+      w.dgm[i] = mp + D;
+      w.grad[13 + i] = -dot(ah, F) + D * (-B * sd - K * imp * q);
     }
-    {
-      float r17[17] = {a_mc[0], a_mc[1], a_mc[2], a_F[0], a_F[1], a_F[2], a_T[0], a_T[1], a_T[2],
-                       a_I[0], a_I[1], a_I[2], a_I[3], a_I[4], a_I[5], a_q, a_v};
-      bsumk(r17);
-#pragma unroll
-      for (int k = 0; k < 3; k++) { a_mc[k] = r17[k]; a_F[k] = r17[3 + k]; a_T[k] = r17[6 + k]; }
-#pragma unroll
-      for (int k = 0; k < 6; k++) a_I[k] = r17[9 + k];
-      a_q = r17[15]; a_v = r17[16];
-    }
+    tsum_to(a, lane, w.r3);
+    env_sync();
     // tendon equality: sum q = 0
+    const float a_q = w.r3[15], a_v = w.r3[16];
+    S4[0] = w.r3[17]; S4[1] = w.r3[18]; S4[2] = w.r3[19]; S4[3] = w.r3[20];
     float K, B, imp;
     kbi(dm.solref[0], dm.solref[1], a_q, &K, &B, &imp);
-    float Dt = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * dm.tendon_iw);
-    float areft = -B * a_v - K * imp * a_q;
-    float mtot = np * m + dm.center_mass;
+    const float Dt = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * dm.tendon_iw);
+    const float areft = -B * a_v - K * imp * a_q;
     if (tid == 0) {
-      w.Dt = Dt; w.areft = areft; w.mtot = mtot;
-      w.mc[0] = a_mc[0]; w.mc[1] = a_mc[1]; w.mc[2] = a_mc[2];
+      const float mtot = np * mp + dm.center_mass;
+      const v3 mc = ld3(w.r3);
+      w.Dt = Dt; w.areft = areft;
       // M_ff: [v (world); omega (body)]
       // rotational inertia: parallel-axis part (depends on q) + constant part (capsules about their COM, centre geom)
-      float It[9] = {a_I[0] + dm.rot_I[0], a_I[3] + dm.rot_I[3], a_I[4] + dm.rot_I[4], a_I[3] + dm.rot_I[3], a_I[1] + dm.rot_I[1],
-                     a_I[5] + dm.rot_I[5], a_I[4] + dm.rot_I[4], a_I[5] + dm.rot_I[5], a_I[2] + dm.rot_I[2]};
-      for (int a = 0; a < 36; a++) w.Mff[a] = 0.f;
-      for (int a = 0; a < 3; a++) w.Mff[a * 6 + a] = mtot;
+      float It[9] = {w.r3[9] + dm.rot_I[0],  w.r3[12] + dm.rot_I[3], w.r3[13] + dm.rot_I[4], w.r3[12] + dm.rot_I[3], w.r3[10] + dm.rot_I[1],
+                     w.r3[14] + dm.rot_I[5], w.r3[13] + dm.rot_I[4], w.r3[14] + dm.rot_I[5], w.r3[11] + dm.rot_I[2]};
+      for (int k = 0; k < 36; k++) w.Mff[k] = 0.f;
+      for (int k = 0; k < 3; k++) w.Mff[k * 6 + k] = mtot;
       // M_v,omega = -R [mc]x  ;  [mc]x = [[0,-z,y],[z,0,-x],[-y,x,0]]
-      float X[9] = {0, -a_mc[2], a_mc[1], a_mc[2], 0, -a_mc[0], -a_mc[1], a_mc[0], 0}, RX[9];
+      float X[9] = {0, -mc.z, mc.y, mc.z, 0, -mc.x, -mc.y, mc.x, 0}, RX[9];
       mm3(R, X, RX);
-      for (int a = 0; a < 3; a++)
-        for (int b = 0; b < 3; b++) { w.Mff[a * 6 + 3 + b] = -RX[3 * a + b]; w.Mff[(3 + b) * 6 + a] = -RX[3 * a + b]; }
-      for (int a = 0; a < 3; a++)
-        for (int b = 0; b < 3; b++) w.Mff[(3 + a) * 6 + 3 + b] = It[3 * a + b];
+      for (int r = 0; r < 3; r++)
+        for (int b = 0; b < 3; b++) { w.Mff[r * 6 + 3 + b] = -RX[3 * r + b]; w.Mff[(3 + b) * 6 + r] = -RX[3 * r + b]; }
+      for (int r = 0; r < 3; r++)
+        for (int b = 0; b < 3; b++) w.Mff[(3 + r) * 6 + 3 + b] = It[3 * r + b];
+      // the same block with a WORLD-frame angular velocity (what the preconditioner works in): -[R mc]x and R I R^T
+      {
+        v3 rm = mv(R, mc);
+        float RI[9], Iw[9], Rt[9] = {R[0], R[3], R[6], R[1], R[4], R[7], R[2], R[5], R[8]};
+        mm3(R, It, RI);
+        mm3(RI, Rt, Iw);
+        float* M = w.Mfw;
+        M[tri6(0, 0)] = mtot; M[tri6(0, 1)] = 0.f; M[tri6(0, 2)] = 0.f; M[tri6(1, 1)] = mtot; M[tri6(1, 2)] = 0.f; M[tri6(2, 2)] = mtot;
+        M[tri6(0, 3)] = 0.f;   M[tri6(0, 4)] = rm.z;  M[tri6(0, 5)] = -rm.y;
+        M[tri6(1, 3)] = -rm.z; M[tri6(1, 4)] = 0.f;   M[tri6(1, 5)] = rm.x;
+        M[tri6(2, 3)] = rm.y;  M[tri6(2, 4)] = -rm.x; M[tri6(2, 5)] = 0.f;
+        M[tri6(3, 3)] = Iw[0]; M[tri6(3, 4)] = Iw[1]; M[tri6(3, 5)] = Iw[2]; M[tri6(4, 4)] = Iw[4]; M[tri6(4, 5)] = Iw[5]; M[tri6(5, 5)] = Iw[8];
+      }
       // bias of the free body
-      v3 sF = mk(a_F[0], a_F[1], a_F[2]), sT = mk(a_T[0], a_T[1], a_T[2]);
+      v3 sF = ld3(w.r3 + 3), sT = ld3(w.r3 + 6);
       v3 bv = mv(R, sF) - dm.center_mass * ld3(dm.g);
       v3 Iw = symv(dm.rot_I, wl);
       v3 bw = sT + cross(wl, Iw);
@@ -263,18 +321,23 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     env_sync();
     // "smooth" pair equalities (carry solrefsmooth = (-stiffness, -damping) of this episode)
     for (int pr = tid; pr < dm.npair; pr += NT) {
-      int a = eq_pairs[2 * pr], b = eq_pairs[2 * pr + 1];
-      float pos = w.qs[a] - w.qs[b], vel = w.hs[13 + a] - w.hs[13 + b], K2, B2, imp2;
+      int ia = eq_pairs[2 * pr], ib = eq_pairs[2 * pr + 1];
+      float pos = w.qs[ia] - w.qs[ib], vel = w.hs[13 + ia] - w.hs[13 + ib], K2, B2, imp2;
       kbi(ksm, bsm, pos, &K2, &B2, &imp2);
-      float D = 1.f / fmaxf(1e-15f, (1.f - imp2) / imp2 * (pt.iw_dof[a] + pt.iw_dof[b]));
+      float D = 1.f / fmaxf(1e-15f, (1.f - imp2) / imp2 * (pt.iw_dof[ia] + pt.iw_dof[ib]));
       w.Dp[pr] = D;
       if (pr == 0) w.Dp[dm.npair] = 0.f; // the slot empty neighbour entries point at
       float ar = D * (-B2 * vel - K2 * imp2 * pos);
-      atomicAdd(&w.grad[13 + a], ar); atomicAdd(&w.grad[13 + b], -ar);
-      atomicAdd(&w.dg[a], D); atomicAdd(&w.dg[b], D);
+      atomicAdd(&w.grad[13 + ia], ar); atomicAdd(&w.grad[13 + ib], -ar);
     }
     env_sync();
-    for (int i = tid; i < np; i += NT) { w.grad[13 + i] += w.Dt * w.areft; w.dg0[i] = w.dg[i] + w.Dt; }
+    for (int i = tid; i < np; i += NT) {
+      const int2* row = reinterpret_cast<const int2*>(pt.nbrpk + 6 * i);
+      int2 e01 = row[0], e23 = row[1], e45 = row[2];
+      float sd = w.Dp[e01.x >> 16] + w.Dp[e01.y >> 16] + w.Dp[e23.x >> 16] + w.Dp[e23.y >> 16] + w.Dp[e45.x >> 16] + w.Dp[e45.y >> 16];
+      w.grad[13 + i] += Dt * areft;
+      w.dgm[i] += sd;
+    }
   }
   if (tid < 7) {
     w.grad[lane] = w.ab[AB_QS + lane];
@@ -340,17 +403,10 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
           }
         }
         unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
-        int before = 0, total = __popc(b0) + __popc(b1);
-        if (WPE > 1) { // cross-warp exclusive prefix of the per-warp hit counts (keeps the particle order)
-          int(*cb) = w.cnt2[rphase];
-          rphase ^= 1;
-          if (lane == 0) cb[wrp] = total;
-          __syncthreads();
-          total = 0;
-#pragma unroll
-          for (int q = 0; q < WPE; q++) { if (q < wrp) before += cb[q]; total += cb[q]; }
-        }
-        int slot = ncon + before + __popc(b0 & lt) + __popc(b1 & lt);
+        int total = __popc(b0) + __popc(b1);
+        int slot = ncon + __popc(b0 & lt) + __popc(b1 & lt);
+        // owner slot of the slider: its first contact (the same thread handles slider i in both passes)
+        if ((h0 || h1) && slot < DEV_MAXC && w.cslot[i] < 0) w.cslot[i] = (short)slot;
         if (h0 && slot < DEV_MAXC) {
           w.cpos[0][slot] = p0.x; w.cpos[1][slot] = p0.y; w.cpos[2][slot] = p0.z;
           w.cn[0][slot] = n0.x; w.cn[1][slot] = n0.y; w.cn[2][slot] = n0.z;
@@ -401,76 +457,65 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     w.cjv[0][c] = -B * dot(nn, rel) - K * imp * w.cdist[c];
     w.cjv[1][c] = -B * dot(t1, rel);
     w.cjv[2][c] = -B * dot(t2, rel);
+    w.czone[c] = 255; // "unknown": the first gradient evaluation always reports a change
   }
   env_sync();
 
   // ------------------------------------------------------------------ helpers (lambdas over the warp)
-  // out = (M + E) in
-  auto applyH = [&](const float* in, float* out) {
-    float sx = 0.f, cl[3] = {0, 0, 0};
-    v3 ivl = mk(0, 0, 0);
+  // out = (M + E) in, in ONE pass: the two slider sums of `in` it needs (S4) are produced by whoever produced `in`.
+  // With q != nullptr also accumulates q[0] += in.Hx, q[1] += in.out (this lane's share).
+  auto applyH = [&](const float* in, float* out, float* q) {
     if (dm.soft) {
-      ivl = mtv(R, ld3(in + 7)); // R^T in_v
-      PRAGMA_HOT
+      const v3 ivl = mtv(R, ld3(in + 7)); // R^T in_v
+      const float Dt = w.Dt, dts = Dt * S4[0];
       for (int i = tid; i < np; i += NT) {
         float xi = in[13 + i];
         v3 ah = ld3(pt.axis + 3 * i);
-        sx += xi;
-        cl[0] += dm.part_mass * ah.x * xi; cl[1] += dm.part_mass * ah.y * xi; cl[2] += dm.part_mass * ah.z * xi;
-      }
-      {
-        float r4[4] = {sx, cl[0], cl[1], cl[2]};
-        bsumk(r4);
-        sx = r4[0]; cl[0] = r4[1]; cl[1] = r4[2]; cl[2] = r4[3];
-      }
-      PRAGMA_HOT
-      for (int i = tid; i < np; i += NT) {
-        float xi = in[13 + i];
-        v3 ah = ld3(pt.axis + 3 * i);
-        float acc = dm.part_mass * (dot(ah, ivl) + xi) + w.df[i] * xi + w.Dt * sx;
         // 6 packed (pair << 16 | neighbour) entries, three 8-byte loads issued back to back, no data-dependent branch
         const int2* row = reinterpret_cast<const int2*>(pt.nbrpk + 6 * i);
         int2 e01 = row[0], e23 = row[1], e45 = row[2];
         int ee[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
+        float acc = mp * dot(ah, ivl) + w.dgm[i] * xi + dts;
 #pragma unroll
-        for (int k = 0; k < 6; k++) acc += w.Dp[ee[k] >> 16] * (xi - in[13 + (ee[k] & 0xffff)]);
+        for (int k = 0; k < 6; k++) acc -= w.Dp[ee[k] >> 16] * in[13 + (ee[k] & 0xffff)];
         out[13 + i] = acc;
+        if (q) { q[0] += xi * w.Hx[13 + i]; q[1] += xi * acc; }
       }
     }
-    if (tid < 7) {
+    if (tid < 13) {
+      float s = 0.f;
+      if (tid < 7) {
+#pragma unroll
+        for (int j = 0; j < 7; j++) s += w.ab[AB_M + lane * 7 + j] * in[j];
+      } else if (dm.soft) {
+        int r = lane - 7;
+#pragma unroll
+        for (int c = 0; c < 6; c++) s += w.Mff[r * 6 + c] * in[7 + c];
+        if (r < 3) s += w.R[3 * r] * S4[1] + w.R[3 * r + 1] * S4[2] + w.R[3 * r + 2] * S4[3];
+      }
+      if (tid < 7 || dm.soft) {
+        out[lane] = s;
+        if (q) { q[0] += in[lane] * w.Hx[lane]; q[1] += in[lane] * s; }
+      }
+    }
+    // dv[0..5] = Jsite in_arm ; dv[6..8] = in_v ; dv[9..11] = R in_omega
+    if (tid >= 16 && tid < 22) {
+      int r = lane - 16;
       float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < 7; j++) s += w.ab[AB_M + lane * 7 + j] * in[j];
-      out[lane] = s;
-    } else if (tid < 13 && dm.soft) {
-      int r = lane - 7;
-      float s = 0.f;
-#pragma unroll
-      for (int c = 0; c < 6; c++) s += w.Mff[r * 6 + c] * in[7 + c];
-      if (r < 3) s += R[3 * r] * cl[0] + R[3 * r + 1] * cl[1] + R[3 * r + 2] * cl[2];
-      out[lane] = s;
+      for (int j = 0; j < 7; j++) s += w.ab[AB_JSITE + r * 7 + j] * in[j];
+      w.dv[r] = s;
+    } else if (tid >= 22 && tid < 25) {
+      w.dv[6 + lane - 22] = dm.soft ? in[7 + lane - 22] : 0.f;
+    } else if (tid >= 25 && tid < 28) {
+      int r = lane - 25;
+      w.dv[9 + r] = dm.soft ? w.R[3 * r] * in[10] + w.R[3 * r + 1] * in[11] + w.R[3 * r + 2] * in[12] : 0.f;
     }
     env_sync();
   };
-  // dv[0..5] = Jsite in_arm ; dv[6..8] = in_v ; dv[9..11] = R in_omega
-  auto dense_vel = [&](const float* in) {
-    if (tid < 6) {
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < 7; j++) s += w.ab[AB_JSITE + lane * 7 + j] * in[j];
-      w.dv[lane] = s;
-    } else if (tid < 9) {
-      w.dv[lane] = dm.soft ? in[7 + lane - 6] : 0.f;
-    } else if (tid < 12) {
-      int r = lane - 9;
-      w.dv[lane] = dm.soft ? R[3 * r] * in[10] + R[3 * r + 1] * in[11] + R[3 * r + 2] * in[12] : 0.f;
-    }
-    env_sync();
-  };
-  // out[j][c] = (J in)_c for the 3 rows of each contact (needs dense_vel(in) first)
+  // out[j][c] = (J in)_c for the 3 rows of each contact (needs dv of `in`, written by applyH)
   auto contactJ = [&](const float* in, float (*out)[DEV_MAXC], bool sub_aref) {
     v3 V = ld3(w.dv), W = ld3(w.dv + 3), iv = ld3(w.dv + 6), iw = ld3(w.dv + 9);
-    PRAGMA_HOT
     for (int c = tid; c < ncon; c += NT) {
       int type = w.ctype[c], i = w.cpart[c];
       v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), t1, t2;
@@ -484,20 +529,19 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     }
     env_sync();
   };
-  // grad = Hx - rhs - J^T f(jar); also returns probe wrench (force, torque about the site) via w.red[12..17]
-  auto update_grad = [&]() -> bool {
-    PRAGMA_HOT
-    for (int i = tid; i < QPAD; i += NT) w.grad[i] = i < nv ? w.Hx[i] : 0.f;
-    env_sync();
-    bool changed = false;
-    float g[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // particle-side (force, torque about P), probe-side (force, torque about site)
-    PRAGMA_HOT
+  // grad (= Hx on entry) -= J^T f(jar).  Lands in w.rg: [0..5] torso wrench about P, [6..11] probe wrench about the site,
+  // [12] zone changes, [13] hx2, [14] rhs2 (the caller's two riders).
+  auto update_grad = [&](float hx2, float rhs2) {
+    float g[15];
+#pragma unroll
+    for (int k = 0; k < 15; k++) g[k] = 0.f;
+    g[13] = hx2; g[14] = rhs2;
     for (int c = tid; c < ncon; c += NT) {
       int type = w.ctype[c], i = w.cpart[c], zone;
       float fr, mu, f0, f1, f2, Dn = w.cD[c];
       contact_params(type, fr, mu);
       cone_force(w.cjar[0][c], w.cjar[1][c], w.cjar[2][c], Dn, Dn * dm.impratio, mu, fr, f0, f1, f2, zone);
-      changed |= (zone != (int)w.czone[c]);
+      if (zone != (int)w.czone[c]) g[12] += 1.f;
       w.czone[c] = (unsigned char)zone;
       if (zone == 0) continue;
       v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), t1, t2;
@@ -513,18 +557,12 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         g[6] += Fw.x; g[7] += Fw.y; g[8] += Fw.z; g[9] += T.x; g[10] += T.y; g[11] += T.z;
       }
     }
-    float g13[13];
-#pragma unroll
-    for (int k = 0; k < 12; k++) g13[k] = g[k];
-    g13[12] = changed ? 1.f : 0.f;
-    bsumk(g13);
-#pragma unroll
-    for (int k = 0; k < 12; k++) g[k] = g13[k];
-    changed = g13[12] > 0.f;
+    tsum_to(g, lane, w.rg);
+    env_sync();
     if (tid < 7) {
       float s = 0.f;
 #pragma unroll
-      for (int r = 0; r < 6; r++) s += w.ab[AB_JSITE + r * 7 + lane] * g[6 + r];
+      for (int r = 0; r < 6; r++) s += w.ab[AB_JSITE + r * 7 + lane] * w.rg[6 + r];
       // joint limit row
       float sg = w.lsign[lane];
       if (sg != 0.f) {
@@ -533,76 +571,86 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       }
       w.grad[lane] -= s;
     } else if (tid < 10 && dm.soft) {
-      w.grad[lane] -= g[lane - 7];
+      w.grad[lane] -= w.rg[lane - 7];
     } else if (tid < 13 && dm.soft) {
       int r = lane - 10; // R^T torque
-      w.grad[lane] -= R[r] * g[3] + R[3 + r] * g[4] + R[6 + r] * g[5];
+      w.grad[lane] -= w.R[r] * w.rg[3] + w.R[3 + r] * w.rg[4] + w.R[6 + r] * w.rg[5];
     }
+    env_sync();
+  };
+  // pg = P^-1 grad  (arm: dense 7x7 Cholesky; torso: arrow with the 6x6 Schur complement, solved with a WORLD-frame angular part).
+  // A slider without contacts couples to the free body through m a_i only; the few with contacts add their owner slot's (K a, r x K a).
+  // Lands in w.rp[9] = grad.pg_old and in w.rq: [0] grad.pg, [1] |grad|^2, [2..5] the slider sums of pg (the next S4).
+  auto precond = [&]() {
+    float a[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) a[k] = 0.f;
+    for (int i = tid; i < np; i += NT) {
+      float g = w.grad[13 + i], gi = g * w.dg[i];
+      v3 ah = ld3(pt.axis + 3 * i);
+      a[0] += ah.x * gi; a[1] += ah.y * gi; a[2] += ah.z * gi;
+      a[9] += g * w.pg[13 + i];
+      w.pg[13 + i] = gi;
+      int cs = w.cslot[i];
+      if (cs >= 0) {
+        a[3] += w.sk[0][cs] * gi; a[4] += w.sk[1][cs] * gi; a[5] += w.sk[2][cs] * gi;
+        a[6] += w.sc[0][cs] * gi; a[7] += w.sc[1][cs] * gi; a[8] += w.sc[2][cs] * gi;
+      }
+    }
+    if (tid < 13) a[9] += w.grad[lane] * w.pg[lane];
+    tsum_to(a, lane, w.rp);
+    env_sync();
+    float gd[13]; // dense part of the gradient
+#pragma unroll
+    for (int k = 0; k < 13; k++) gd[k] = w.grad[k];
+    float ya[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) ya[j] = gd[j];
+    chol7_solve<7>(w.Pa, ya);
+    float y[6] = {0, 0, 0, 0, 0, 0};
+    v3 yl = mk(0, 0, 0), yb = mk(0, 0, 0);
+    if (dm.soft) {
+      v3 tv = mp * mv(R, ld3(w.rp)) + ld3(w.rp + 3), gw = mv(R, mk(gd[10], gd[11], gd[12])) - ld3(w.rp + 6);
+      y[0] = gd[7] - tv.x; y[1] = gd[8] - tv.y; y[2] = gd[9] - tv.z; y[3] = gw.x; y[4] = gw.y; y[5] = gw.z;
+      chol7_solve<6>(w.Sf, y);
+      yl = mtv(R, mk(y[0], y[1], y[2]));
+      yb = mtv(R, mk(y[3], y[4], y[5])); // back to the body frame
+    }
+    float b[6] = {0, 0, 0, 0, 0, 0};
     if (tid == 0) {
 #pragma unroll
-      for (int k = 0; k < 6; k++) w.red[12 + k] = g[6 + k];
-    }
-    env_sync();
-    return changed;
-  };
-  // pg = P^-1 grad  (arm: dense 7x7 Cholesky; torso: arrow with the 6x6 Schur complement Sf)
-  auto precond = [&]() {
-    float t[6] = {0, 0, 0, 0, 0, 0};
-    if (dm.soft) {
-      PRAGMA_HOT
-      for (int i = tid; i < np; i += NT) {
-        v3 ah = ld3(pt.axis + 3 * i), aw = mv(R, ah);
-        v3 kk = mk(w.kx[i], w.ky[i], w.kz[i]);
-        v3 bv = kk + dm.part_mass * aw;
-        v3 cr = mv(R, ld3(pt.pos + 3 * i) + (w.qs[i] - dm.cap_r) * ah);
-        v3 bw = mtv(R, cross(cr, kk));
-        float gi = w.grad[13 + i] / w.dg[i];
-        t[0] += bv.x * gi; t[1] += bv.y * gi; t[2] += bv.z * gi; t[3] += bw.x * gi; t[4] += bw.y * gi; t[5] += bw.z * gi;
-      }
-      bsumk(t);
-      float y[6];
+      for (int j = 0; j < 7; j++) { w.pg[j] = ya[j]; b[0] += gd[j] * ya[j]; b[1] += gd[j] * gd[j]; }
+      if (dm.soft) {
+        w.pg[7] = y[0]; w.pg[8] = y[1]; w.pg[9] = y[2]; w.pg[10] = yb.x; w.pg[11] = yb.y; w.pg[12] = yb.z;
+        b[0] += gd[7] * y[0] + gd[8] * y[1] + gd[9] * y[2] + gd[10] * yb.x + gd[11] * yb.y + gd[12] * yb.z;
 #pragma unroll
-      for (int k = 0; k < 6; k++) y[k] = w.grad[7 + k] - t[k];
-      chol_solve<6>(w.Sf, y);
-      if (tid < 6) w.pg[7 + lane] = y[lane];
-      PRAGMA_HOT
-      for (int i = tid; i < np; i += NT) {
-        v3 ah = ld3(pt.axis + 3 * i), aw = mv(R, ah);
-        v3 kk = mk(w.kx[i], w.ky[i], w.kz[i]);
-        v3 bv = kk + dm.part_mass * aw;
-        v3 cr = mv(R, ld3(pt.pos + 3 * i) + (w.qs[i] - dm.cap_r) * ah);
-        v3 bw = mtv(R, cross(cr, kk));
-        float by = bv.x * y[0] + bv.y * y[1] + bv.z * y[2] + bw.x * y[3] + bw.y * y[4] + bw.z * y[5];
-        w.pg[13 + i] = (w.grad[13 + i] - by) / w.dg[i];
+        for (int k = 7; k < 13; k++) b[1] += gd[k] * gd[k];
       }
     }
-    {
-      float ya[7];
-#pragma unroll
-      for (int j = 0; j < 7; j++) ya[j] = w.grad[j];
-      chol_solve<7>(w.Pa, ya);
-      if (tid < 7) w.pg[lane] = ya[lane];
+    for (int i = tid; i < np; i += NT) {
+      float g = w.grad[13 + i];
+      v3 ah = ld3(pt.axis + 3 * i);
+      float by = mp * dot(ah, yl);
+      int cs = w.cslot[i];
+      if (cs >= 0)
+        by += w.sk[0][cs] * y[0] + w.sk[1][cs] * y[1] + w.sk[2][cs] * y[2] + w.sc[0][cs] * y[3] + w.sc[1][cs] * y[4] + w.sc[2][cs] * y[5];
+      float p = w.pg[13 + i] - by * w.dg[i];
+      w.pg[13 + i] = p;
+      b[0] += g * p; b[1] += g * g; b[2] += p;
+      b[3] += mp * ah.x * p; b[4] += mp * ah.y * p; b[5] += mp * ah.z * p;
     }
+    tsum_to(b, lane, w.rq);
     env_sync();
   };
-  auto vdot = [&](const float* a, const float* b) {
-    float s = 0.f;
-PRAGMA_HOT
-    for (int i = tid; i < nv; i += NT) s += a[i] * b[i];
-    return bsum(s);
-  };
 
-  // ------------------------------------------------------------------ K6: nonlinear PCG; pass -1 evaluates the warm start
-  for (int c = tid; c < ncon; c += NT) w.czone[c] = 255; // "unknown": the first update always reports a change
-  for (int i = tid; i < QPAD; i += NT) w.s[i] = 0.f;
-  env_sync();
-
-  // preconditioner from the current active set (contact zones); rebuilt when the zones change
+  // preconditioner from the current active set (contact zones); rebuilt when the zones change.  Runs 1-3 times per solve.
   auto build_precond = [&]() {
-    // Runs 1-3 times per solve: written for SMALL CODE (rolled loops, stack arrays), not for speed, so that it does not
-    // evict the CG loop body from the instruction cache.
 #pragma unroll 1
-    for (int i = tid; i < np; i += NT) { w.dg[i] = w.dg0[i]; w.kx[i] = 0.f; w.ky[i] = 0.f; w.kz[i] = 0.f; }
+    for (int i = tid; i < np; i += NT) w.dg[i] = w.dgm[i] + w.Dt;
+#pragma unroll 1
+    for (int c = tid; c < ncon; c += NT) {
+      w.sk[0][c] = 0.f; w.sk[1][c] = 0.f; w.sk[2][c] = 0.f; w.sc[0][c] = 0.f; w.sc[1][c] = 0.f; w.sc[2][c] = 0.f;
+    }
     env_sync();
     float acc[42]; // packed upper triangles of the 6x6 wrench-space Hessians: [0..20] torso side (about P), [21..41] probe side (about the site)
 #pragma unroll
@@ -634,10 +682,11 @@ PRAGMA_HOT
           for (int b2 = 0; b2 < 3; b2++) Hc[3 * a2 + b2] = Dm * g3[a2] * g3[b2];
         Hc[4] += kk * (1.f - u1 * u1); Hc[5] -= kk * u1 * u2; Hc[7] -= kk * u1 * u2; Hc[8] += kk * (1.f - u2 * u2);
       }
-      if (type != 2) { // slider of this particle: k_i += K a_i, dg_i += a_i^T K a_i with K = F^T Hc F
+      if (type != 2) { // slider of this particle: (K a_i) into its owner slot, a_i^T K a_i onto its diagonal, K = F^T Hc F
         v3 aw = mv(R, ld3(pt.axis + 3 * i));
         v3 fa = mv(F, aw), hf = mv(Hc, fa), ka = mtv(F, hf);
-        atomicAdd(&w.kx[i], ka.x); atomicAdd(&w.ky[i], ka.y); atomicAdd(&w.kz[i], ka.z);
+        int own = w.cslot[i];
+        atomicAdd(&w.sk[0][own], ka.x); atomicAdd(&w.sk[1][own], ka.y); atomicAdd(&w.sk[2][own], ka.z);
         atomicAdd(&w.dg[i], dot(fa, hf));
       }
       // wrench-space Hessian A^T K A with A = [I, -[r]x]: W[a] = [f_a ; r x f_a], U = Hc W, acc += W^T U (upper triangle)
@@ -661,29 +710,24 @@ PRAGMA_HOT
       if (type != 2) accum(acc, pos - P);
       if (type != 0) accum(acc + 21, pos - site);
     }
+    // entry l of each packed triangle lands in lane l
+    float kf, kp;
     {
       float(&lo21)[21] = *reinterpret_cast<float(*)[21]>(acc);
       float(&hi21)[21] = *reinterpret_cast<float(*)[21]>(acc + 21);
-      bsumk(lo21);
-      bsumk(hi21);
+      kf = tsum(lo21, lane);
+      kp = tsum(hi21, lane);
     }
+    if (lane < 21) w.Kp[lane] = kp;
     env_sync();
     // arm block: Pa = M + Jsite^T Kp Jsite + limits   (lanes 0..6, column `lane`)
     if (tid < 7) {
-      float Kp6[36];
-      {
-        int idx = 21;
-#pragma unroll
-        for (int a2 = 0; a2 < 6; a2++)
-#pragma unroll
-          for (int b2 = a2; b2 < 6; b2++) { Kp6[a2 * 6 + b2] = acc[idx]; Kp6[b2 * 6 + a2] = acc[idx]; idx++; }
-      }
       float KJ[6]; // (Kp Jsite)[:, lane]
 #pragma unroll
       for (int a2 = 0; a2 < 6; a2++) {
         float sacc = 0.f;
 #pragma unroll
-        for (int b2 = 0; b2 < 6; b2++) sacc += Kp6[a2 * 6 + b2] * w.ab[AB_JSITE + b2 * 7 + lane];
+        for (int b2 = 0; b2 < 6; b2++) sacc += w.Kp[tri6(a2, b2)] * w.ab[AB_JSITE + b2 * 7 + lane];
         KJ[a2] = sacc;
       }
 #pragma unroll
@@ -695,7 +739,7 @@ PRAGMA_HOT
         w.Pa[r2 * 7 + lane] = sacc;
       }
     }
-    // torso block: Sf = Mff + Kf(local) - sum_i b_i b_i^T / dg_i
+    // torso block (world-frame omega): Sf = Mfw + Kf - sum_i b_i b_i^T / dg_i,  b_i = [m a_i + K a_i ; r_i x K a_i]
     if (dm.soft) {
       float sb[21];
 #pragma unroll
@@ -703,68 +747,59 @@ PRAGMA_HOT
 #pragma unroll 1
       for (int i = tid; i < np; i += NT) {
         v3 ah = ld3(pt.axis + 3 * i), aw = mv(R, ah);
-        v3 kk = mk(w.kx[i], w.ky[i], w.kz[i]);
-        v3 bv = kk + dm.part_mass * aw;
-        v3 cr = mv(R, ld3(pt.pos + 3 * i) + (w.qs[i] - dm.cap_r) * ah);
-        v3 bw = mtv(R, cross(cr, kk));
-        float b6[6] = {bv.x, bv.y, bv.z, bw.x, bw.y, bw.z}, inv = 1.f / w.dg[i];
-        int idx = 0;
+        float inv = 1.f / w.dg[i];
+        w.dg[i] = inv;
+        v3 bv = mp * aw;
+        int cs = w.cslot[i];
+        if (cs >= 0) {
+          v3 kk = mk(w.sk[0][cs], w.sk[1][cs], w.sk[2][cs]);
+          v3 cr = mv(R, ld3(pt.pos + 3 * i) + (w.qs[i] - dm.cap_r) * ah);
+          v3 ck = cross(cr, kk);
+          w.sc[0][cs] = ck.x; w.sc[1][cs] = ck.y; w.sc[2][cs] = ck.z;
+          bv = bv + kk;
+          float b6[6] = {bv.x, bv.y, bv.z, ck.x, ck.y, ck.z};
 #pragma unroll
-        for (int a2 = 0; a2 < 6; a2++)
+          for (int a2 = 0; a2 < 6; a2++)
 #pragma unroll
-          for (int c2 = a2; c2 < 6; c2++) { sb[idx] += b6[a2] * b6[c2] * inv; idx++; }
+            for (int c2 = (a2 < 3 ? 3 : a2); c2 < 6; c2++) sb[tri6(a2, c2)] += b6[a2] * b6[c2] * inv;
+        }
+        sb[tri6(0, 0)] += bv.x * bv.x * inv; sb[tri6(0, 1)] += bv.x * bv.y * inv; sb[tri6(0, 2)] += bv.x * bv.z * inv;
+        sb[tri6(1, 1)] += bv.y * bv.y * inv; sb[tri6(1, 2)] += bv.y * bv.z * inv; sb[tri6(2, 2)] += bv.z * bv.z * inv;
       }
-      bsumk(sb);
-      if (tid == 0) {
-        // rotate the angular part of Kf to the body frame: T = diag(I, R); Kl = T^T Kf T.  Scratch: hs[0..95] (dead here)
-        float* Kf = w.hs; float* Kl = w.hs + 36; float* sbs = w.hs + 72;
-        {
-          int idx = 0;
-#pragma unroll
-          for (int a2 = 0; a2 < 6; a2++)
-#pragma unroll
-            for (int b2 = a2; b2 < 6; b2++) { Kf[a2 * 6 + b2] = acc[idx]; Kf[b2 * 6 + a2] = acc[idx]; sbs[idx] = sb[idx]; idx++; }
-        }
-        int idx = 0;
-#pragma unroll 1
-        for (int a2 = 0; a2 < 3; a2++)
-#pragma unroll 1
-          for (int b2 = 0; b2 < 3; b2++) {
-            Kl[a2 * 6 + b2] = Kf[a2 * 6 + b2];
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-            for (int k = 0; k < 3; k++) s1 += Kf[a2 * 6 + 3 + k] * w.R[3 * k + b2];
-            Kl[a2 * 6 + 3 + b2] = s1; Kl[(3 + b2) * 6 + a2] = s1;
-#pragma unroll 1
-            for (int k = 0; k < 3; k++)
-#pragma unroll 1
-              for (int l = 0; l < 3; l++) s2 += w.R[3 * k + a2] * Kf[(3 + k) * 6 + 3 + l] * w.R[3 * l + b2];
-            Kl[(3 + a2) * 6 + 3 + b2] = s2;
-          }
-#pragma unroll 1
-        for (int attempt = 0; attempt < 2; attempt++) {
-          idx = 0;
-#pragma unroll 1
-          for (int a2 = 0; a2 < 6; a2++)
-#pragma unroll 1
-            for (int b2 = a2; b2 < 6; b2++) {
-              float v = w.Mff[a2 * 6 + b2] + Kl[a2 * 6 + b2] - (attempt == 0 ? sbs[idx] : 0.f);
-              idx++;
-              w.Sf[a2 * 6 + b2] = v; w.Sf[b2 * 6 + a2] = v;
-            }
-          if (chol_rolled(w.Sf, 6)) break;
-          // fall back to the free block without the slider coupling
-#pragma unroll 1
-          for (int i = 0; i < np; i++) { w.kx[i] = 0.f; w.ky[i] = 0.f; w.kz[i] = 0.f; }
-        }
+      float sbl = tsum(sb, lane);
+      if (lane < 21) {
+        int ab2 = c_tri6[lane], a2 = ab2 >> 4, b2 = ab2 & 15;
+        float v = w.Mfw[lane] + kf - sbl;
+        w.Sf[a2 * 7 + b2] = v; w.Sf[b2 * 7 + a2] = v;
       }
     }
     env_sync();
-    if (tid == 0) chol_rolled(w.Pa, 7);
+    // both factorisations at once: lane 0 -> Sf (6x6 padded to 7x7), lane 1 -> Pa
+    if (tid < 2) {
+      bool ok = chol7_inv(tid ? w.Pa : w.Sf);
+      if (!ok && tid == 0) w.bad = 1;
+    }
     env_sync();
+    if (w.bad) { // Sf lost positive definiteness (fp32): fall back to the free block without the slider coupling
+      env_sync();
+#pragma unroll 1
+      for (int c = tid; c < ncon; c += NT) {
+        w.sk[0][c] = 0.f; w.sk[1][c] = 0.f; w.sk[2][c] = 0.f; w.sc[0][c] = 0.f; w.sc[1][c] = 0.f; w.sc[2][c] = 0.f;
+      }
+      if (lane < 21) {
+        int ab2 = c_tri6[lane], a2 = ab2 >> 4, b2 = ab2 & 15;
+        float v = w.Mfw[lane] + kf;
+        w.Sf[a2 * 7 + b2] = v; w.Sf[b2 * 7 + a2] = v;
+      }
+      if (tid == 0) w.bad = 0;
+      env_sync();
+      if (tid == 0) chol7_inv(w.Sf);
+      env_sync();
+    }
   };
 
-  float gpg = 1.f, gnorm = 0.f, rhsn = 0.f;
+  // ------------------------------------------------------------------ K6: nonlinear PCG; pass -1 evaluates the warm start
+  float gpg = 1.f, gnorm = 0.f, rhsn = 0.f, hxn = 0.f;
   int iters = 0, rebuilds = 0;
   const int maxit = mode == 1 ? 2 * dm.iters : dm.iters;
   // every helper has exactly ONE call site (code size: the loop body must stay inside the instruction cache)
@@ -773,34 +808,29 @@ PRAGMA_HOT
     const bool init = it < 0;
     if (!init) {
       // fp32 floor of the gradient is ~eps * (|Hx| + |rhs|): the terms that cancel in it
-      if (gnorm <= dm.tol * (1.f + rhsn + sqrtf(vdot(w.Hx, w.Hx)))) break;
+      if (gnorm <= dm.tol * (1.f + rhsn + hxn)) break;
       iters = it + 1;
     }
     const float* vin = init ? w.x : w.s;
     float* vout = init ? w.Hx : w.hs;
-    applyH(vin, vout);
-    dense_vel(vin);
+    float q12[2] = {0.f, 0.f};
+    applyH(vin, vout, init ? nullptr : q12);
     contactJ(vin, init ? w.cjar : w.cjv, init);
+    float hx2 = 0.f, rhs2 = 0.f;
     if (init) {
-      rhsn = sqrtf(vdot(w.grad, w.grad)); // grad holds rhs until here
-      PRAGMA_HOT
-      for (int i = tid; i < nv; i += NT) w.Hx[i] -= w.grad[i];
+      // grad holds rhs until here
+      for (int i = tid; i < nv; i += NT) {
+        float r = w.grad[i], hx = w.Hx[i] - r;
+        w.Hx[i] = hx; w.grad[i] = hx;
+        rhs2 += r * r; hx2 += hx * hx;
+      }
       env_sync();
     } else {
       // ---- exact line search: Newton on phi'(alpha)
-      float q1 = 0.f, q2 = 0.f;
-      PRAGMA_HOT
-      for (int i = tid; i < nv; i += NT) { q1 += w.s[i] * w.Hx[i]; q2 += w.s[i] * w.hs[i]; }
-      {
-        float r2[2] = {q1, q2};
-        bsumk(r2);
-        q1 = r2[0]; q2 = r2[1];
-      }
-      float alpha = 0.f, lo = 0.f, hi = -1.f, d0abs = 0.f;
+      float q1 = 0.f, q2 = 0.f, alpha = 0.f, lo = 0.f, hi = -1.f, d0abs = 0.f;
 #pragma unroll 1
       for (int ls = 0; ls < 8; ls++) {
         float d1 = 0.f, d2 = 0.f;
-        PRAGMA_HOT
         for (int c = tid; c < ncon; c += NT) {
           float fr, mu, a1, a2, Dn = w.cD[c];
           contact_params(w.ctype[c], fr, mu);
@@ -813,10 +843,14 @@ PRAGMA_HOT
           if (jar < 0.f) { d1 += w.lD[lane] * jar * jv; d2 += w.lD[lane] * jv * jv; }
         }
         {
-          float r2[2] = {d1, d2};
-          bsumk(r2);
-          d1 = r2[0] + q1 + alpha * q2;
-          d2 = r2[1] + q2;
+          // the quadratic part (s.Hx, s.Hs) rides on every reduction: constant cost, one call site
+          float r4[4] = {d1, d2, q12[0], q12[1]};
+          tsum_to(r4, lane, w.rl);
+          env_sync();
+          q1 = w.rl[2]; q2 = w.rl[3];
+          d1 = w.rl[0] + q1 + alpha * q2;
+          d2 = w.rl[1] + q2;
+          env_sync(); // w.rl is rewritten by the next pass
         }
         if (ls == 0) d0abs = fabsf(d1);
         if (fabsf(d1) <= 1e-5f * d0abs || !(d2 > 0.f)) break;
@@ -827,16 +861,20 @@ PRAGMA_HOT
         if (an == alpha) break;
         alpha = an;
       }
-      PRAGMA_HOT
-      for (int i = tid; i < nv; i += NT) { w.x[i] += alpha * w.s[i]; w.Hx[i] += alpha * w.hs[i]; }
-      PRAGMA_HOT
+      for (int i = tid; i < nv; i += NT) {
+        float hx = w.Hx[i] + alpha * w.hs[i];
+        w.x[i] += alpha * w.s[i]; w.Hx[i] = hx; w.grad[i] = hx;
+        hx2 += hx * hx;
+      }
       for (int c = tid; c < ncon; c += NT) {
         w.cjar[0][c] += alpha * w.cjv[0][c]; w.cjar[1][c] += alpha * w.cjv[1][c]; w.cjar[2][c] += alpha * w.cjv[2][c];
       }
       env_sync();
     }
-    bool changed = update_grad();
-    float gpo = init ? 0.f : vdot(w.grad, w.pg); // with the previous pg (Polak-Ribiere)
+    update_grad(hx2, rhs2);
+    const bool changed = w.rg[12] > 0.f;
+    hxn = sqrtf(w.rg[13]);
+    if (init) rhsn = sqrtf(w.rg[14]);
     bool restart = init;
     // soft scene: rebuild when the active set moved; rigid scene (7 unknowns): exact Hessian every iteration = Newton
     if (init || (changed && rebuilds < dm.max_rebuilds) || (!dm.soft && ncon > 0)) {
@@ -845,17 +883,18 @@ PRAGMA_HOT
       restart = true;
     }
     precond();
-    float gpn = vdot(w.grad, w.pg);
-    gnorm = sqrtf(vdot(w.grad, w.grad));
+    const float gpo = w.rp[9], gpn = w.rq[0]; // grad.pg with the previous pg (Polak-Ribiere) and with the new one
+    gnorm = sqrtf(w.rq[1]);
     float beta = restart ? 0.f : fmaxf(0.f, (gpn - gpo) / fmaxf(gpg, 1e-30f));
     gpg = gpn;
-    PRAGMA_HOT
+#pragma unroll
+    for (int k = 0; k < 4; k++) S4[k] = -w.rq[2 + k] + beta * S4[k];
     for (int i = tid; i < nv; i += NT) w.s[i] = -w.pg[i] + beta * w.s[i];
     env_sync();
   }
 
   // ------------------------------------------------------------------ K8: probe wrench, F/T torque
-  v3 cfrc = mk(w.red[12], w.red[13], w.red[14]), ctq = mk(w.red[15], w.red[16], w.red[17]);
+  v3 cfrc = ld3(w.rg + 6), ctq = ld3(w.rg + 9); // probe wrench of the last gradient evaluation
   v3 ft;
   {
     float t3[3];
@@ -870,24 +909,33 @@ PRAGMA_HOT
   }
   bool in_contact = false;
   for (int c = tid; c < ncon; c += NT) in_contact |= (w.ctype[c] == 1);
-  in_contact = bsum(in_contact ? 1.f : 0.f) > 0.f;
+  in_contact = __any_sync(0xffffffffu, in_contact);
 
   // ------------------------------------------------------------------ K7: integrate (mj_Euler) and write the state back
   if (mode == 0) {
-    // arm: implicit joint damping, (M + h D) qacc' = M qacc, through a dense 7x7 Cholesky on lane 0
-    if (tid == 0) {
-      float A[49], b[7];
+    // arm: implicit joint damping, (M + h D) qacc' = M qacc, through a dense 7x7 Cholesky (w.Pa and w.dv are free again)
+    if (tid < 7) {
+      float s = 0.f;
 #pragma unroll
-      for (int r = 0; r < 7; r++) {
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 7; j++) { A[r * 7 + j] = w.ab[AB_M + r * 7 + j] + (r == j ? h * dm.arm_damp : 0.f); s += w.ab[AB_M + r * 7 + j] * w.x[j]; }
-        b[r] = s;
+      for (int j = 0; j < 7; j++) {
+        float mj = w.ab[AB_M + lane * 7 + j];
+        w.Pa[lane * 7 + j] = mj + (lane == j ? h * dm.arm_damp : 0.f);
+        s += mj * w.x[j];
       }
-      chol<7>(A);
-      chol_solve<7>(A, b);
+      w.dv[lane] = s;
+    }
+    env_sync();
+    if (tid == 0) chol7_inv(w.Pa);
+    env_sync();
+    {
+      float b[7];
 #pragma unroll
-      for (int j = 0; j < 7; j++) w.qdarm[j] += h * b[j];
+      for (int j = 0; j < 7; j++) b[j] = w.dv[j];
+      chol7_solve<7>(w.Pa, b);
+      if (tid == 0) {
+#pragma unroll
+        for (int j = 0; j < 7; j++) w.qdarm[j] += h * b[j];
+      }
     }
     env_sync();
     for (int i = tid; i < nv; i += NT) wm_g[i] = w.x[i];
@@ -929,7 +977,9 @@ PRAGMA_HOT
   }
 
   // divergence guard (MuJoCo resets on bad qacc): a non-finite solution ends the episode, the reset wipes the state
-  const float xnorm2 = vdot(w.x, w.x);
+  float xnorm2 = 0.f;
+  for (int i = tid; i < nv; i += NT) xnorm2 += w.x[i] * w.x[i];
+  xnorm2 = wsum(xnorm2);
   // ------------------------------------------------------------------ K9: task epilogue (lane 0)
   if (tid == 0) {
     float* ts = w.ts;
