@@ -168,7 +168,7 @@ def run_cuda(args):
         per_gpu = args.envs
     else:
         per_gpu = 4096 if world == 1 else 65536 // world
-    env = BatchedUltrasound(per_gpu, device=dev, seed=SEED, env_id_offset=rank * per_gpu, solver_iterations=args.iters, **ENV_OPTS)
+    env = BatchedUltrasound(per_gpu, device=dev, seed=SEED, env_id_offset=rank * per_gpu, solver_iterations=args.iters, precond_rebuilds=args.rebuilds, **ENV_OPTS)
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(SEED + rank)
@@ -268,6 +268,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: BASELINE configs)")
     ap.add_argument("--iters", type=int, default=40, help="solver iteration cap")
+    ap.add_argument("--rebuilds", type=int, default=0, help="preconditioner rebuilds allowed per solve (0: library default)")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=40)

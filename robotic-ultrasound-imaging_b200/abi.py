@@ -141,6 +141,7 @@ def make_config(
     env_id_offset: int = 0,
     solver_iterations: int = 40,
     solver_tolerance: float = 3e-6,
+    precond_rebuilds: int = 0,
     reset_eef_bias=ART_RESET_EEF_BIAS,
 ) -> UsimConfig:
     """Translate the ``suite.make("Ultrasound", ...)`` kwargs (rl_config.yaml:18-57,
@@ -158,6 +159,7 @@ def make_config(
     c.deterministic_trajectory = int(bool(deterministic_trajectory))
     c.uncouple_pos_ori = int(bool(cc.get("uncouple_pos_ori", True)))
     c.solver_iterations = int(solver_iterations)
+    c.precond_rebuilds = int(precond_rebuilds)
     c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     c.control_freq = float(control_freq)
     c.kp[:] = _six(cc.get("kp", 150))

@@ -43,7 +43,7 @@ struct __align__(16) WS {
   float r3[24], rg[16], rp[16], rq[8], rl[4];          // landing zones of the warp reductions (one per call site)
   float lsign[7], lD[7], laref[7];
   float Dt, areft;
-  int ncon, bad;
+  int ncon;
 };
 
 __device__ __forceinline__ void env_sync() { __syncwarp(); }
@@ -137,38 +137,36 @@ __device__ __forceinline__ void seg_seg(v3 p1, v3 q1, v3 p2, v3 q2, v3& c1, v3& 
   c2 = p2 + t * d2;
 }
 
-// In-place Cholesky of a 7x7 (row-major, both triangles valid on entry) held in shared memory, done in registers by ONE thread.
-// The factor is left in the lower triangle with its diagonal INVERTED (the solves multiply).
-__device__ __forceinline__ bool chol7_inv(float* A) {
-  float L[28];
+// In-place Cholesky of TWO 7x7 matrices (row-major, pitch 7, both triangles valid on entry) held in shared memory, by one warp:
+// one matrix row per lane (lanes 0-6 -> A0, lanes 8-14 -> A1), right-looking, rows in registers, columns exchanged by shuffles.
+// The factors are left in the lower triangles with their diagonals INVERTED (the solves multiply).  Returns false in the lanes of a
+// matrix that met a non-positive pivot (the pivot is clamped).  Every loop has a constant trip count: nothing is indexed dynamically.
+__device__ __forceinline__ bool chol7_warp2(float* A0, float* A1, int lane) {
+  const int base = lane & 8, r = lane & 7;
+  const bool act = lane < 16 && r < 7;
+  float* A = base ? A1 : A0;
+  float row[7];
 #pragma unroll
-  for (int i = 0; i < 7; i++)
-#pragma unroll
-    for (int j = 0; j <= i; j++) L[i * (i + 1) / 2 + j] = A[i * 7 + j];
+  for (int k = 0; k < 7; k++) row[k] = act ? A[r * 7 + k] : (k == r ? 1.f : 0.f);
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 7; j++) {
-    float s = L[j * (j + 1) / 2 + j];
+    float d = __shfl_sync(0xffffffffu, row[j], base + j);
+    if (!(d > 0.f)) { ok = false; d = 1e-20f; }
+    const float inv = rsqrtf(d);
+    const float l = row[j] * inv; // L[r][j] for r > j, sqrt(d) for r == j, unused above the diagonal
 #pragma unroll
-    for (int k = 0; k < j; k++) s -= L[j * (j + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
-    if (!(s > 0.f)) { ok = false; s = 1e-20f; }
-    float inv = rsqrtf(s);
-    L[j * (j + 1) / 2 + j] = inv;
-#pragma unroll
-    for (int i = j + 1; i < 7; i++) {
-      float t = L[i * (i + 1) / 2 + j];
-#pragma unroll
-      for (int k = 0; k < j; k++) t -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
-      L[i * (i + 1) / 2 + j] = t * inv;
+    for (int k = 0; k < 7; k++) {
+      if (k > j) row[k] -= l * __shfl_sync(0xffffffffu, l, base + k);
     }
+    row[j] = r == j ? inv : l;
   }
 #pragma unroll
-  for (int i = 0; i < 7; i++)
-#pragma unroll
-    for (int j = 0; j <= i; j++) A[i * 7 + j] = L[i * (i + 1) / 2 + j];
+  for (int k = 0; k < 7; k++)
+    if (act && k <= r) A[r * 7 + k] = row[k];
   return ok;
 }
-// x <- (L L^T)^-1 x for the leading N x N block of a factor written by chol7_inv (row pitch 7)
+// x <- (L L^T)^-1 x for the leading N x N block of a factor written by chol7_warp2 (row pitch 7)
 template <int N>
 __device__ __forceinline__ void chol7_solve(const float* L, float* x) {
 #pragma unroll
@@ -218,7 +216,6 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
   }
   for (int i = tid; i < 49; i += NT) w.Sf[i] = (i % 8 == 0) ? 1.f : 0.f; // identity: row/col 6 of the padded 6x6 stay like this
   if (tid < 7) w.qdarm[tid] = qv_g[tid];
-  if (tid == 0) w.bad = 0;
   float quat[4] = {1, 0, 0, 0};
   if (dm.soft) {
     if (tid < 6) w.vf[tid] = qv_g[7 + tid];
@@ -721,6 +718,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     if (lane < 21) w.Kp[lane] = kp;
     env_sync();
     // arm block: Pa = M + Jsite^T Kp Jsite + limits   (lanes 0..6, column `lane`)
+    float pa_col[7] = {0, 0, 0, 0, 0, 0, 0};
     if (tid < 7) {
       float KJ[6]; // (Kp Jsite)[:, lane]
 #pragma unroll
@@ -736,10 +734,12 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
 #pragma unroll
         for (int a2 = 0; a2 < 6; a2++) sacc += w.ab[AB_JSITE + a2 * 7 + r2] * KJ[a2];
         if (r2 == lane && w.lsign[lane] != 0.f) sacc += w.lD[lane];
+        pa_col[r2] = sacc;
         w.Pa[r2 * 7 + lane] = sacc;
       }
     }
     // torso block (world-frame omega): Sf = Mfw + Kf - sum_i b_i b_i^T / dg_i,  b_i = [m a_i + K a_i ; r_i x K a_i]
+    float sbl = 0.f;
     if (dm.soft) {
       float sb[21];
 #pragma unroll
@@ -766,36 +766,31 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         sb[tri6(0, 0)] += bv.x * bv.x * inv; sb[tri6(0, 1)] += bv.x * bv.y * inv; sb[tri6(0, 2)] += bv.x * bv.z * inv;
         sb[tri6(1, 1)] += bv.y * bv.y * inv; sb[tri6(1, 2)] += bv.y * bv.z * inv; sb[tri6(2, 2)] += bv.z * bv.z * inv;
       }
-      float sbl = tsum(sb, lane);
-      if (lane < 21) {
+      sbl = tsum(sb, lane);
+    }
+    // both factorisations at once (Sf is a 6x6 padded to 7x7).  If Sf lost positive definiteness (fp32) the second attempt
+    // drops the slider coupling: the free block alone is positive definite.
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; attempt++) {
+      if (dm.soft && lane < 21) {
         int ab2 = c_tri6[lane], a2 = ab2 >> 4, b2 = ab2 & 15;
-        float v = w.Mfw[lane] + kf - sbl;
+        float v = w.Mfw[lane] + kf - (attempt == 0 ? sbl : 0.f);
         w.Sf[a2 * 7 + b2] = v; w.Sf[b2 * 7 + a2] = v;
       }
-    }
-    env_sync();
-    // both factorisations at once: lane 0 -> Sf (6x6 padded to 7x7), lane 1 -> Pa
-    if (tid < 2) {
-      bool ok = chol7_inv(tid ? w.Pa : w.Sf);
-      if (!ok && tid == 0) w.bad = 1;
-    }
-    env_sync();
-    if (w.bad) { // Sf lost positive definiteness (fp32): fall back to the free block without the slider coupling
       env_sync();
+      bool ok = chol7_warp2(w.Sf, w.Pa, lane);
+      if (__all_sync(0xffffffffu, ok || lane >= 8)) break;
 #pragma unroll 1
       for (int c = tid; c < ncon; c += NT) {
         w.sk[0][c] = 0.f; w.sk[1][c] = 0.f; w.sk[2][c] = 0.f; w.sc[0][c] = 0.f; w.sc[1][c] = 0.f; w.sc[2][c] = 0.f;
       }
-      if (lane < 21) {
-        int ab2 = c_tri6[lane], a2 = ab2 >> 4, b2 = ab2 & 15;
-        float v = w.Mfw[lane] + kf;
-        w.Sf[a2 * 7 + b2] = v; w.Sf[b2 * 7 + a2] = v;
+      // (Pa was factorised in place by the first attempt: the second one must see the matrix again)
+      if (tid < 7) {
+#pragma unroll
+        for (int r2 = 0; r2 < 7; r2++) w.Pa[r2 * 7 + lane] = pa_col[r2];
       }
-      if (tid == 0) w.bad = 0;
-      env_sync();
-      if (tid == 0) chol7_inv(w.Sf);
-      env_sync();
     }
+    env_sync();
   };
 
   // ------------------------------------------------------------------ K6: nonlinear PCG; pass -1 evaluates the warm start
@@ -925,7 +920,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       w.dv[lane] = s;
     }
     env_sync();
-    if (tid == 0) chol7_inv(w.Pa);
+    chol7_warp2(w.Pa, w.Pa, lane);
     env_sync();
     {
       float b[7];
