@@ -50,14 +50,11 @@ struct DevModel {
   float eef_bias[3];
 };
 
-// per-particle tables in global memory (read only)
+// per-particle tables in global memory (read only, shared by every env: L1/L2 resident), one 16-byte load per record
 struct PartTables {
-  const float* pos;   // [npart][3] torso frame
-  const float* axis;  // [npart][3]
-  const float* iw_dof;  // [npart] dof_invweight0 of the slider
-  const float* iw_body; // [npart] body_invweight0 (translational)
-  const int* nbr;     // [npart][6]
-  const int* nbrpk;   // [npart][6] packed (pair << 16) | neighbour; empty slots = (npair << 16) | self
+  const float4* ax4; // [npart] slider axis (torso frame) xyz, w = dof_invweight0 of the slider
+  const float4* ps4; // [npart] rest position (torso frame) xyz, w = body_invweight0 (translational)
+  const int4* nb4;   // [npart] up to 4 grid neighbours, packed (pair << 16) | neighbour; empty slots = (npair << 16) | self
 };
 
 __constant__ DevModel dm;  // single translation unit (usim.cu)
@@ -68,6 +65,7 @@ struct v3 {
 };
 __device__ __forceinline__ v3 mk(float x, float y, float z) { return v3{x, y, z}; }
 __device__ __forceinline__ v3 ld3(const float* p) { return v3{p[0], p[1], p[2]}; }
+__device__ __forceinline__ v3 xyz(float4 a) { return v3{a.x, a.y, a.z}; }
 __device__ __forceinline__ void st3(float* p, v3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
 __device__ __forceinline__ v3 operator+(v3 a, v3 b) { return v3{a.x + b.x, a.y + b.y, a.z + b.z}; }
 __device__ __forceinline__ v3 operator-(v3 a, v3 b) { return v3{a.x - b.x, a.y - b.y, a.z - b.z}; }

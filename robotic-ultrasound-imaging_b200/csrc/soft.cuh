@@ -188,8 +188,8 @@ __device__ __forceinline__ void chol7_solve(const float* L, float* x) {
 // mode: 0 = env step, 1 = reset forward (no integration; initialises the running statistics)
 __global__ void __launch_bounds__(NT, 8) solve_kernel(
     int n, int mode, const uint8_t* __restrict__ mask, float* __restrict__ qpos, float* __restrict__ qvel, float* __restrict__ warm,
-    float* __restrict__ task, const float* __restrict__ armbuf, PartTables pt, const int* __restrict__ eq_pairs,
-    const short* __restrict__ nbr_pair, float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
+    float* __restrict__ task, const float* __restrict__ armbuf, PartTables pt, const int2* __restrict__ eq_pairs,
+    float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
     float* __restrict__ diag, int* __restrict__ ncon_out, int* __restrict__ geom1_out, int* __restrict__ geom2_out,
     float* __restrict__ dist_out, int* __restrict__ diverged) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
 #pragma unroll
     for (int k = 0; k < 21; k++) a[k] = 0.f;
     for (int i = tid; i < np; i += NT) {
-      v3 ah = ld3(pt.axis + 3 * i), r0 = ld3(pt.pos + 3 * i);
+      const float4 a4 = pt.ax4[i];
+      v3 ah = xyz(a4), r0 = xyz(pt.ps4[i]);
       float q = w.qs[i], sd = w.hs[13 + i], xi = w.x[13 + i];
       v3 c = r0 + (q - off) * ah;
       a[0] += mp * c.x; a[1] += mp * c.y; a[2] += mp * c.z;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       // "fix" equality of this slider
       float K, B, imp;
       kbi(dm.solref[0], dm.solref[1], q, &K, &B, &imp);
-      float D = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * pt.iw_dof[i]);
+      float D = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * a4.w);
       w.dgm[i] = mp + D;
       w.grad[13 + i] = -dot(ah, F) + D * (-B * sd - K * imp * q);
     }
@@ -318,10 +319,11 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     env_sync();
     // "smooth" pair equalities (carry solrefsmooth = (-stiffness, -damping) of this episode)
     for (int pr = tid; pr < dm.npair; pr += NT) {
-      int ia = eq_pairs[2 * pr], ib = eq_pairs[2 * pr + 1];
+      const int2 pr2 = eq_pairs[pr];
+      const int ia = pr2.x, ib = pr2.y;
       float pos = w.qs[ia] - w.qs[ib], vel = w.hs[13 + ia] - w.hs[13 + ib], K2, B2, imp2;
       kbi(ksm, bsm, pos, &K2, &B2, &imp2);
-      float D = 1.f / fmaxf(1e-15f, (1.f - imp2) / imp2 * (pt.iw_dof[ia] + pt.iw_dof[ib]));
+      float D = 1.f / fmaxf(1e-15f, (1.f - imp2) / imp2 * (pt.ax4[ia].w + pt.ax4[ib].w));
       w.Dp[pr] = D;
       if (pr == 0) w.Dp[dm.npair] = 0.f; // the slot empty neighbour entries point at
       float ar = D * (-B2 * vel - K2 * imp2 * pos);
@@ -329,9 +331,8 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     }
     env_sync();
     for (int i = tid; i < np; i += NT) {
-      const int2* row = reinterpret_cast<const int2*>(pt.nbrpk + 6 * i);
-      int2 e01 = row[0], e23 = row[1], e45 = row[2];
-      float sd = w.Dp[e01.x >> 16] + w.Dp[e01.y >> 16] + w.Dp[e23.x >> 16] + w.Dp[e23.y >> 16] + w.Dp[e45.x >> 16] + w.Dp[e45.y >> 16];
+      const int4 e = pt.nb4[i];
+      float sd = w.Dp[e.x >> 16] + w.Dp[e.y >> 16] + w.Dp[e.z >> 16] + w.Dp[e.w >> 16];
       w.grad[13 + i] += Dt * areft;
       w.dgm[i] += sd;
     }
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         v3 p0 = mk(0, 0, 0), p1 = mk(0, 0, 0), n0 = mk(0, 0, -1);
         float d0 = 0.f, d1 = 0.f;
         if (i < np) {
-          v3 ah = ld3(pt.axis + 3 * i), r0 = ld3(pt.pos + 3 * i);
+          v3 ah = xyz(pt.ax4[i]), r0 = xyz(pt.ps4[i]);
           float q = w.qs[i];
           v3 eo = P + mv(R, r0 + (q - dm.cap_r) * ah), ei = P + mv(R, r0 + (q - dm.cap_r - 2.f * dm.cap_hl) * ah);
           if (pass == 0) {
@@ -443,9 +444,9 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     v3 rel = mk(0, 0, 0);
     float diagA = 0.f;
     if (type != 2) {
-      v3 aw = mv(R, ld3(pt.axis + 3 * i));
+      v3 aw = mv(R, xyz(pt.ax4[i]));
       rel = rel - (vlin + cross(ww, pos - P) + w.hs[13 + i] * aw);
-      diagA += pt.iw_body[i];
+      diagA += pt.ps4[i].w;
     }
     if (type != 0) { rel = rel + Vs + cross(Ws, pos - site); diagA += dm.iw_probe; }
     float K, B, imp;
@@ -467,14 +468,12 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       const float Dt = w.Dt, dts = Dt * S4[0];
       for (int i = tid; i < np; i += NT) {
         float xi = in[13 + i];
-        v3 ah = ld3(pt.axis + 3 * i);
-        // 6 packed (pair << 16 | neighbour) entries, three 8-byte loads issued back to back, no data-dependent branch
-        const int2* row = reinterpret_cast<const int2*>(pt.nbrpk + 6 * i);
-        int2 e01 = row[0], e23 = row[1], e45 = row[2];
-        int ee[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
+        v3 ah = xyz(pt.ax4[i]);
+        // 4 packed (pair << 16 | neighbour) entries in one 16-byte load, no data-dependent branch
+        const int4 e = pt.nb4[i];
         float acc = mp * dot(ah, ivl) + w.dgm[i] * xi + dts;
-#pragma unroll
-        for (int k = 0; k < 6; k++) acc -= w.Dp[ee[k] >> 16] * in[13 + (ee[k] & 0xffff)];
+        acc -= w.Dp[e.x >> 16] * in[13 + (e.x & 0xffff)]; acc -= w.Dp[e.y >> 16] * in[13 + (e.y & 0xffff)];
+        acc -= w.Dp[e.z >> 16] * in[13 + (e.z & 0xffff)]; acc -= w.Dp[e.w >> 16] * in[13 + (e.w & 0xffff)];
         out[13 + i] = acc;
         if (q) { q[0] += xi * w.Hx[13 + i]; q[1] += xi * acc; }
       }
@@ -518,7 +517,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), t1, t2;
       make_frame(nn, &t1, &t2);
       v3 rel = mk(0, 0, 0);
-      if (type != 2) rel = rel - (iv + cross(iw, pos - P) + in[13 + i] * mv(R, ld3(pt.axis + 3 * i)));
+      if (type != 2) rel = rel - (iv + cross(iw, pos - P) + in[13 + i] * mv(R, xyz(pt.ax4[i])));
       if (type != 0) rel = rel + V + cross(W, pos - site);
       float o0 = dot(nn, rel), o1 = dot(t1, rel), o2 = dot(t2, rel);
       if (sub_aref) { o0 -= w.cjv[0][c]; o1 -= w.cjv[1][c]; o2 -= w.cjv[2][c]; }
@@ -547,7 +546,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       if (type != 2) {
         v3 Fp = -Fw, T = cross(pos - P, Fp);
         g[0] += Fp.x; g[1] += Fp.y; g[2] += Fp.z; g[3] += T.x; g[4] += T.y; g[5] += T.z;
-        atomicAdd(&w.grad[13 + i], -dot(mv(R, ld3(pt.axis + 3 * i)), Fp));
+        atomicAdd(&w.grad[13 + i], -dot(mv(R, xyz(pt.ax4[i])), Fp));
       }
       if (type != 0) {
         v3 T = cross(pos - site, Fw);
@@ -584,10 +583,10 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     for (int k = 0; k < 10; k++) a[k] = 0.f;
     for (int i = tid; i < np; i += NT) {
       float g = w.grad[13 + i], gi = g * w.dg[i];
-      v3 ah = ld3(pt.axis + 3 * i);
+      v3 ah = xyz(pt.ax4[i]);
       a[0] += ah.x * gi; a[1] += ah.y * gi; a[2] += ah.z * gi;
       a[9] += g * w.pg[13 + i];
-      w.pg[13 + i] = gi;
+      w.hs[13 + i] = gi; // hs is free between the line search and the next applyH
       int cs = w.cslot[i];
       if (cs >= 0) {
         a[3] += w.sk[0][cs] * gi; a[4] += w.sk[1][cs] * gi; a[5] += w.sk[2][cs] * gi;
@@ -626,12 +625,16 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     }
     for (int i = tid; i < np; i += NT) {
       float g = w.grad[13 + i];
-      v3 ah = ld3(pt.axis + 3 * i);
+      v3 ah = xyz(pt.ax4[i]);
       float by = mp * dot(ah, yl);
       int cs = w.cslot[i];
       if (cs >= 0)
         by += w.sk[0][cs] * y[0] + w.sk[1][cs] * y[1] + w.sk[2][cs] * y[2] + w.sc[0][cs] * y[3] + w.sc[1][cs] * y[4] + w.sc[2][cs] * y[5];
-      float p = w.pg[13 + i] - by * w.dg[i];
+      // slider block D - W (W: the pair couplings) inverted to second order, D^-1 + D^-1 W D^-1: hs holds D^-1 grad
+      const int4 e = pt.nb4[i];
+      float nb = w.Dp[e.x >> 16] * w.hs[13 + (e.x & 0xffff)] + w.Dp[e.y >> 16] * w.hs[13 + (e.y & 0xffff)] +
+                 w.Dp[e.z >> 16] * w.hs[13 + (e.z & 0xffff)] + w.Dp[e.w >> 16] * w.hs[13 + (e.w & 0xffff)];
+      float p = w.hs[13 + i] + (nb - by) * w.dg[i];
       w.pg[13 + i] = p;
       b[0] += g * p; b[1] += g * g; b[2] += p;
       b[3] += mp * ah.x * p; b[4] += mp * ah.y * p; b[5] += mp * ah.z * p;
@@ -680,7 +683,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         Hc[4] += kk * (1.f - u1 * u1); Hc[5] -= kk * u1 * u2; Hc[7] -= kk * u1 * u2; Hc[8] += kk * (1.f - u2 * u2);
       }
       if (type != 2) { // slider of this particle: (K a_i) into its owner slot, a_i^T K a_i onto its diagonal, K = F^T Hc F
-        v3 aw = mv(R, ld3(pt.axis + 3 * i));
+        v3 aw = mv(R, xyz(pt.ax4[i]));
         v3 fa = mv(F, aw), hf = mv(Hc, fa), ka = mtv(F, hf);
         int own = w.cslot[i];
         atomicAdd(&w.sk[0][own], ka.x); atomicAdd(&w.sk[1][own], ka.y); atomicAdd(&w.sk[2][own], ka.z);
@@ -746,14 +749,14 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       for (int k = 0; k < 21; k++) sb[k] = 0.f;
 #pragma unroll 1
       for (int i = tid; i < np; i += NT) {
-        v3 ah = ld3(pt.axis + 3 * i), aw = mv(R, ah);
+        v3 ah = xyz(pt.ax4[i]), aw = mv(R, ah);
         float inv = 1.f / w.dg[i];
         w.dg[i] = inv;
         v3 bv = mp * aw;
         int cs = w.cslot[i];
         if (cs >= 0) {
           v3 kk = mk(w.sk[0][cs], w.sk[1][cs], w.sk[2][cs]);
-          v3 cr = mv(R, ld3(pt.pos + 3 * i) + (w.qs[i] - dm.cap_r) * ah);
+          v3 cr = mv(R, xyz(pt.ps4[i]) + (w.qs[i] - dm.cap_r) * ah);
           v3 ck = cross(cr, kk);
           w.sc[0][cs] = ck.x; w.sc[1][cs] = ck.y; w.sc[2][cs] = ck.z;
           bv = bv + kk;

@@ -32,10 +32,9 @@ struct usim_handle {
   float* cdist = nullptr;
   int* diverged = nullptr; // number of env steps that produced a non-finite solution (episode force-ended)
   // model tables
-  float *part_pos = nullptr, *part_axis = nullptr, *iw_dof = nullptr, *iw_body = nullptr;
-  int *nbr = nullptr, *eq_pairs = nullptr;
-  short* nbr_pair = nullptr;
-  int* nbrpk = nullptr;
+  float4 *ax4 = nullptr, *ps4 = nullptr; // (axis, dof_invweight0), (rest position, body_invweight0)
+  int4* nb4 = nullptr;                   // packed neighbour / pair stencil
+  int2* eq_pairs = nullptr;
   // staging for the host-buffer path
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_tobs = nullptr;
   uint8_t* h_done = nullptr;
@@ -190,12 +189,25 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
     for (size_t e = 0; e < N; e++) t[e * USIM_TASK_DIM + USIM_TS_DONE] = 1.f;
     CKH(cudaMemcpy(h->task, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
-  CKH(upload(&h->part_pos, ppos)); CKH(upload(&h->part_axis, paxis)); CKH(upload(&h->iw_dof, iwd)); CKH(upload(&h->iw_body, iwb));
-  CKH(upload(&h->nbr, nbr)); CKH(upload(&h->eq_pairs, pairs)); CKH(upload(&h->nbr_pair, nbrp));
   {
-    std::vector<int> pk(nbr.size());
-    for (size_t e = 0; e < nbr.size(); e++) pk[e] = nbr[e] >= 0 ? ((int)nbrp[e] << 16) | nbr[e] : (d.npair << 16) | (int)(e / 6);
-    CKH(upload(&h->nbrpk, pk));
+    const int np = d.npart;
+    std::vector<float4> a4(np), p4(np);
+    std::vector<int4> n4(np);
+    std::vector<int2> p2(d.npair);
+    for (int i = 0; i < np; i++) {
+      a4[i] = make_float4(paxis[3 * i], paxis[3 * i + 1], paxis[3 * i + 2], iwd[i]);
+      p4[i] = make_float4(ppos[3 * i], ppos[3 * i + 1], ppos[3 * i + 2], iwb[i]);
+      int e[4], cnt = 0;
+      for (int k = 0; k < 6; k++)
+        if (nbr[6 * i + k] >= 0) {
+          if (cnt == 4 || nbrp[6 * i + k] < 0) { g_err = "usim_create: the composite's pair stencil has more than 4 neighbours per element (compiled limit)"; usim_destroy(h); return -1; }
+          e[cnt++] = ((int)nbrp[6 * i + k] << 16) | nbr[6 * i + k];
+        }
+      for (; cnt < 4; cnt++) e[cnt] = (d.npair << 16) | i;
+      n4[i] = make_int4(e[0], e[1], e[2], e[3]);
+    }
+    for (int p = 0; p < d.npair; p++) p2[p] = make_int2(pairs[2 * p], pairs[2 * p + 1]);
+    CKH(upload(&h->ax4, a4)); CKH(upload(&h->ps4, p4)); CKH(upload(&h->nb4, n4)); CKH(upload(&h->eq_pairs, p2));
   }
   CKH(cudaMallocHost((void**)&h->h_act, N * USIM_MAX_ACTION * sizeof(float)));
   CKH(cudaMallocHost((void**)&h->h_obs, N * USIM_OBS_DIM * sizeof(float)));
@@ -224,8 +236,8 @@ int usim_destroy(usim_handle* h) {
   cudaDeviceSynchronize();
   if (g_active == h) g_active = nullptr;
   for (auto& p : h->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-  void* dev[] = {h->diverged, h->qpos, h->qvel, h->warm, h->task, h->armbuf, h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->part_pos,
-                 h->part_axis, h->iw_dof, h->iw_body, h->nbr, h->eq_pairs, h->nbr_pair, h->nbrpk, h->d_act, h->d_obs, h->d_tobs, h->d_rew,
+  void* dev[] = {h->diverged, h->qpos, h->qvel, h->warm, h->task, h->armbuf, h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->ax4,
+                 h->ps4, h->nb4, h->eq_pairs, h->d_act, h->d_obs, h->d_tobs, h->d_rew,
                  h->d_done, h->d_resetmask};
   for (void* p : dev) if (p) cudaFree(p);
   void* host[] = {h->h_act, h->h_obs, h->h_tobs, h->h_rew, h->h_done};
@@ -235,7 +247,7 @@ int usim_destroy(usim_handle* h) {
   return 0;
 }
 
-static PartTables tables(const usim_handle* h) { return PartTables{h->part_pos, h->part_axis, h->iw_dof, h->iw_body, h->nbr, h->nbrpk}; }
+static PartTables tables(const usim_handle* h) { return PartTables{h->ax4, h->ps4, h->nb4}; }
 
 // launches: the DevModel symbol is per-process; re-upload if another handle changed it
 static int activate(usim_handle* h) {
@@ -261,7 +273,7 @@ static int launch_forward(usim_handle* h, int mode, const uint8_t* mask, const f
     CK(cudaEventRecord(e0, s));
   }
   solve_kernel<<<n, NT, h->smem, s>>>(
-      n, mode, mask, h->qpos, h->qvel, h->warm, h->task, h->armbuf, tables(h), h->eq_pairs, h->nbr_pair, obs, rew, done, h->diag,
+      n, mode, mask, h->qpos, h->qvel, h->warm, h->task, h->armbuf, tables(h), h->eq_pairs, obs, rew, done, h->diag,
       h->ncon, h->geom1, h->geom2, h->cdist, h->diverged);
   if (timed) {
     CK(cudaEventRecord(e1, s));
