@@ -88,33 +88,34 @@ __constant__ unsigned char c_tri6[21] = {0x00, 0x01, 0x02, 0x03, 0x04, 0x05, 0x1
                                          0x22, 0x23, 0x24, 0x25, 0x33, 0x34, 0x35, 0x44, 0x45, 0x55};
 __device__ __forceinline__ constexpr int tri6(int a, int b) { return a <= b ? a * 6 - a * (a - 1) / 2 + (b - a) : b * 6 - b * (b - 1) / 2 + (a - b); }
 
-__device__ __forceinline__ void cone_force(float j0, float j1, float j2, float Dn, float Dt, float mu, float fr, float& f0, float& f1,
-                                           float& f2, int& zone) {
-  float N = j0 * mu, U1 = j1 * fr, U2 = j2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
-  if (N >= mu * T || (T <= 0.f && N >= 0.f)) { zone = 0; f0 = f1 = f2 = 0.f; }
-  else if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) { zone = 2; f0 = -Dn * j0; f1 = -Dt * j1; f2 = -Dt * j2; }
-  else {
-    zone = 1;
-    float Dm = Dn / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T;
-    f0 = -Dm * NmT * mu;
-    f1 = -f0 / T * U1 * fr;
-    f2 = -f0 / T * U2 * fr;
-  }
+// Elliptic cone (condim 3) in WORLD coordinates.  The cone is isotropic in the tangent plane (one friction coefficient, one
+// tangential D), so no tangent basis is needed: a contact row triple is kept as the world vector j = J x - aref, split as
+// j = jn n + jt.  Returns the world force on geom2 and the zone (0 = top / inactive, 1 = middle, 2 = bottom / quadratic).
+__device__ __forceinline__ v3 cone_force(v3 j, v3 n, float Dn, float Dt, float mu, float fr, int& zone) {
+  const float jn = dot(j, n);
+  const v3 jt = j - jn * n;
+  const float N = jn * mu, T = fr * norm(jt);
+  if (N >= mu * T || (T <= 0.f && N >= 0.f)) { zone = 0; return mk(0, 0, 0); }
+  if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) { zone = 2; return (-Dn * jn) * n - Dt * jt; }
+  zone = 1;
+  const float Dm = Dn / (mu * mu * (1.f + mu * mu)), f0 = -Dm * (N - mu * T) * mu;
+  return f0 * n - (f0 * fr * fr / T) * jt;
 }
-// first / second directional derivative of the cone cost at jar along jv
-__device__ __forceinline__ void cone_ls(float j0, float j1, float j2, float v0, float v1, float v2, float Dn, float Dt, float mu, float fr,
-                                        float& d1, float& d2) {
-  float N = j0 * mu, U1 = j1 * fr, U2 = j2 * fr, T = sqrtf(U1 * U1 + U2 * U2);
+// first / second directional derivative of the cone cost at j along v
+__device__ __forceinline__ void cone_ls(v3 j, v3 v, v3 n, float Dn, float Dt, float mu, float fr, float& d1, float& d2) {
+  const float jn = dot(j, n), vn = dot(v, n);
+  const v3 jt = j - jn * n, vt = v - vn * n; // explicit tangential parts: |j|^2 - jn^2 would cancel when the load is mostly normal
+  const float tt = dot(jt, jt), tv = dot(jt, vt), vv = dot(vt, vt);
+  const float N = jn * mu, T = fr * sqrtf(tt);
   if (N >= mu * T || (T <= 0.f && N >= 0.f)) { d1 = 0.f; d2 = 0.f; }
   else if (mu * N + T <= 0.f || (T <= 0.f && N < 0.f)) {
-    d1 = Dn * j0 * v0 + Dt * (j1 * v1 + j2 * v2);
-    d2 = Dn * v0 * v0 + Dt * (v1 * v1 + v2 * v2);
+    d1 = Dn * jn * vn + Dt * tv;
+    d2 = Dn * vn * vn + Dt * vv;
   } else {
-    float Dm = Dn / (mu * mu * (1.f + mu * mu)), g = N - mu * T;
-    float Np = mu * v0, U1p = fr * v1, U2p = fr * v2;
-    float Tp = (U1 * U1p + U2 * U2p) / T;
-    float Tpp = (U1p * U1p + U2p * U2p - Tp * Tp) / T;
-    float gp = Np - mu * Tp;
+    const float Dm = Dn / (mu * mu * (1.f + mu * mu)), g = N - mu * T, f2 = fr * fr;
+    const float Tp = f2 * tv / T;
+    const float Tpp = (f2 * vv - Tp * Tp) / T;
+    const float gp = mu * vn - mu * Tp;
     d1 = Dm * g * gp;
     d2 = Dm * (gp * gp - g * mu * Tpp);
   }
@@ -439,8 +440,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
   }
   for (int c = tid; c < ncon; c += NT) {
     int type = w.ctype[c], i = w.cpart[c];
-    v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), t1, t2;
-    make_frame(nn, &t1, &t2);
+    v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]);
     v3 rel = mk(0, 0, 0);
     float diagA = 0.f;
     if (type != 2) {
@@ -452,9 +452,9 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     float K, B, imp;
     kbi(dm.solref[0], dm.solref[1], w.cdist[c], &K, &B, &imp);
     w.cD[c] = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * diagA);
-    w.cjv[0][c] = -B * dot(nn, rel) - K * imp * w.cdist[c];
-    w.cjv[1][c] = -B * dot(t1, rel);
-    w.cjv[2][c] = -B * dot(t2, rel);
+    // aref = -B v_rel - K imp dist n: the normal row carries the position term, the tangential rows only damping
+    v3 ar = (-B) * rel - (K * imp * w.cdist[c]) * nn;
+    w.cjv[0][c] = ar.x; w.cjv[1][c] = ar.y; w.cjv[2][c] = ar.z;
     w.czone[c] = 255; // "unknown": the first gradient evaluation always reports a change
   }
   env_sync();
@@ -509,19 +509,18 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     }
     env_sync();
   };
-  // out[j][c] = (J in)_c for the 3 rows of each contact (needs dv of `in`, written by applyH)
+  // out[.][c] = relative acceleration of the contact point pair (geom2 - geom1) as a WORLD vector, i.e. the 3 rows of J in
+  // before projection on the contact frame (needs dv of `in`, written by applyH)
   auto contactJ = [&](const float* in, float (*out)[DEV_MAXC], bool sub_aref) {
     v3 V = ld3(w.dv), W = ld3(w.dv + 3), iv = ld3(w.dv + 6), iw = ld3(w.dv + 9);
     for (int c = tid; c < ncon; c += NT) {
       int type = w.ctype[c], i = w.cpart[c];
-      v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), t1, t2;
-      make_frame(nn, &t1, &t2);
+      v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]);
       v3 rel = mk(0, 0, 0);
       if (type != 2) rel = rel - (iv + cross(iw, pos - P) + in[13 + i] * mv(R, xyz(pt.ax4[i])));
       if (type != 0) rel = rel + V + cross(W, pos - site);
-      float o0 = dot(nn, rel), o1 = dot(t1, rel), o2 = dot(t2, rel);
-      if (sub_aref) { o0 -= w.cjv[0][c]; o1 -= w.cjv[1][c]; o2 -= w.cjv[2][c]; }
-      out[0][c] = o0; out[1][c] = o1; out[2][c] = o2;
+      if (sub_aref) rel = rel - mk(w.cjv[0][c], w.cjv[1][c], w.cjv[2][c]);
+      out[0][c] = rel.x; out[1][c] = rel.y; out[2][c] = rel.z;
     }
     env_sync();
   };
@@ -534,15 +533,14 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     g[13] = hx2; g[14] = rhs2;
     for (int c = tid; c < ncon; c += NT) {
       int type = w.ctype[c], i = w.cpart[c], zone;
-      float fr, mu, f0, f1, f2, Dn = w.cD[c];
+      float fr, mu, Dn = w.cD[c];
       contact_params(type, fr, mu);
-      cone_force(w.cjar[0][c], w.cjar[1][c], w.cjar[2][c], Dn, Dn * dm.impratio, mu, fr, f0, f1, f2, zone);
+      const v3 nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]);
+      const v3 Fw = cone_force(mk(w.cjar[0][c], w.cjar[1][c], w.cjar[2][c]), nn, Dn, Dn * dm.impratio, mu, fr, zone); // force on geom2
       if (zone != (int)w.czone[c]) g[12] += 1.f;
       w.czone[c] = (unsigned char)zone;
       if (zone == 0) continue;
-      v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), t1, t2;
-      make_frame(nn, &t1, &t2);
-      v3 Fw = f0 * nn + f1 * t1 + f2 * t2; // force on geom2
+      const v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]);
       if (type != 2) {
         v3 Fp = -Fw, T = cross(pos - P, Fp);
         g[0] += Fp.x; g[1] += Fp.y; g[2] += Fp.z; g[3] += T.x; g[4] += T.y; g[5] += T.z;
@@ -659,53 +657,51 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     for (int c = tid; c < ncon; c += NT) {
       int zone = w.czone[c], type = w.ctype[c], i = w.cpart[c];
       if (zone == 0) continue;
-      float Dn = w.cD[c];
-      v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]);
-      float F[9]; // contact frame rows: normal, tangent 1, tangent 2
-      {
-        v3 nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), t1, t2;
-        make_frame(nn, &t1, &t2);
-        st3(F, nn); st3(F + 3, t1); st3(F + 6, t2);
-      }
-      float Hc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // Hessian of the cone cost wrt (jar_n, jar_t1, jar_t2)
-      if (zone == 2) { // bottom zone: quadratic
-        Hc[0] = Dn; Hc[4] = Dn * dm.impratio; Hc[8] = Dn * dm.impratio;
+      const float Dn = w.cD[c], Dtn = Dn * dm.impratio;
+      const v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]);
+      // World Hessian of the cone cost wrt the contact-point acceleration, K = c_i I + c_n n n^T + c_u u u^T + c_g g g^T
+      // (u: unit tangential direction of j, g = mu n - mu fr u the gradient direction of the middle zone)
+      float ci, cnn, cu = 0.f, cg = 0.f;
+      v3 u = mk(0, 0, 0), gv = mk(0, 0, 0);
+      if (zone == 2) { // bottom zone: quadratic, Dn along n and Dt in the tangent plane
+        ci = Dtn; cnn = Dn - Dtn;
       } else { // middle zone: exact Hessian of 0.5 Dm (N - mu T)^2
         float fr, mu;
         contact_params(type, fr, mu);
-        float N = w.cjar[0][c] * mu, U1 = w.cjar[1][c] * fr, U2 = w.cjar[2][c] * fr, T = fmaxf(sqrtf(U1 * U1 + U2 * U2), 1e-20f);
-        float Dm = Dn / (mu * mu * (1.f + mu * mu)), NmT = N - mu * T, u1 = U1 / T, u2 = U2 / T;
-        float g3[3] = {mu, -mu * u1 * fr, -mu * u2 * fr}, kk = -Dm * mu * NmT / T * fr * fr;
-#pragma unroll
-        for (int a2 = 0; a2 < 3; a2++)
-#pragma unroll
-          for (int b2 = 0; b2 < 3; b2++) Hc[3 * a2 + b2] = Dm * g3[a2] * g3[b2];
-        Hc[4] += kk * (1.f - u1 * u1); Hc[5] -= kk * u1 * u2; Hc[7] -= kk * u1 * u2; Hc[8] += kk * (1.f - u2 * u2);
+        const v3 j = mk(w.cjar[0][c], w.cjar[1][c], w.cjar[2][c]);
+        const float jn = dot(j, nn);
+        const v3 jt = j - jn * nn;
+        const float tn = fmaxf(norm(jt), 1e-20f), T = fr * tn, Dm = Dn / (mu * mu * (1.f + mu * mu)), NmT = jn * mu - mu * T;
+        u = (1.f / tn) * jt;
+        gv = mu * nn - (mu * fr) * u;
+        const float kk = -Dm * mu * NmT / T * fr * fr; // curvature of the cone surface, acts on the tangent plane minus u
+        ci = kk; cnn = -kk; cu = -kk; cg = Dm;
       }
-      if (type != 2) { // slider of this particle: (K a_i) into its owner slot, a_i^T K a_i onto its diagonal, K = F^T Hc F
+      float Ks[6]; // xx, xy, xz, yy, yz, zz
+      Ks[0] = ci + cnn * nn.x * nn.x + cu * u.x * u.x + cg * gv.x * gv.x;
+      Ks[1] = cnn * nn.x * nn.y + cu * u.x * u.y + cg * gv.x * gv.y;
+      Ks[2] = cnn * nn.x * nn.z + cu * u.x * u.z + cg * gv.x * gv.z;
+      Ks[3] = ci + cnn * nn.y * nn.y + cu * u.y * u.y + cg * gv.y * gv.y;
+      Ks[4] = cnn * nn.y * nn.z + cu * u.y * u.z + cg * gv.y * gv.z;
+      Ks[5] = ci + cnn * nn.z * nn.z + cu * u.z * u.z + cg * gv.z * gv.z;
+      const v3 K0 = mk(Ks[0], Ks[1], Ks[2]), K1 = mk(Ks[1], Ks[3], Ks[4]), K2 = mk(Ks[2], Ks[4], Ks[5]);
+      if (type != 2) { // slider of this particle: (K a_i) into its owner slot, a_i^T K a_i onto its diagonal
         v3 aw = mv(R, xyz(pt.ax4[i]));
-        v3 fa = mv(F, aw), hf = mv(Hc, fa), ka = mtv(F, hf);
+        v3 ka = mk(dot(K0, aw), dot(K1, aw), dot(K2, aw));
         int own = w.cslot[i];
         atomicAdd(&w.sk[0][own], ka.x); atomicAdd(&w.sk[1][own], ka.y); atomicAdd(&w.sk[2][own], ka.z);
-        atomicAdd(&w.dg[i], dot(fa, hf));
+        atomicAdd(&w.dg[i], dot(aw, ka));
       }
-      // wrench-space Hessian A^T K A with A = [I, -[r]x]: W[a] = [f_a ; r x f_a], U = Hc W, acc += W^T U (upper triangle)
+      // wrench-space Hessian [I; [r]x] K [I, [r]x^T] (force; torque about the reference point), packed upper triangle:
+      // upper-right block rows r x K_i, lower-right block columns r x (column of the upper-right block)
       auto accum = [&](float* A21, v3 r) {
-        float W[18], U[18];
-#pragma unroll
-        for (int a2 = 0; a2 < 3; a2++) {
-          v3 f = ld3(F + 3 * a2), m3 = cross(r, f);
-          st3(W + 6 * a2, f); st3(W + 6 * a2 + 3, m3);
-        }
-#pragma unroll
-        for (int a2 = 0; a2 < 3; a2++)
-#pragma unroll
-          for (int q = 0; q < 6; q++) U[6 * a2 + q] = Hc[3 * a2] * W[q] + Hc[3 * a2 + 1] * W[6 + q] + Hc[3 * a2 + 2] * W[12 + q];
-        int idx = 0;
-#pragma unroll
-        for (int p2 = 0; p2 < 6; p2++)
-#pragma unroll
-          for (int q = p2; q < 6; q++) { A21[idx] += W[p2] * U[q] + W[6 + p2] * U[6 + q] + W[12 + p2] * U[12 + q]; idx++; }
+        const v3 B0 = cross(r, K0), B1 = cross(r, K1), B2 = cross(r, K2); // rows of K [r]x^T
+        const v3 C0 = cross(r, mk(B0.x, B1.x, B2.x)), C1 = cross(r, mk(B0.y, B1.y, B2.y)), C2 = cross(r, mk(B0.z, B1.z, B2.z)); // columns of [r]x K [r]x^T
+        A21[tri6(0, 0)] += Ks[0]; A21[tri6(0, 1)] += Ks[1]; A21[tri6(0, 2)] += Ks[2]; A21[tri6(1, 1)] += Ks[3]; A21[tri6(1, 2)] += Ks[4]; A21[tri6(2, 2)] += Ks[5];
+        A21[tri6(0, 3)] += B0.x; A21[tri6(0, 4)] += B0.y; A21[tri6(0, 5)] += B0.z;
+        A21[tri6(1, 3)] += B1.x; A21[tri6(1, 4)] += B1.y; A21[tri6(1, 5)] += B1.z;
+        A21[tri6(2, 3)] += B2.x; A21[tri6(2, 4)] += B2.y; A21[tri6(2, 5)] += B2.z;
+        A21[tri6(3, 3)] += C0.x; A21[tri6(3, 4)] += C1.x; A21[tri6(3, 5)] += C2.x; A21[tri6(4, 4)] += C1.y; A21[tri6(4, 5)] += C2.y; A21[tri6(5, 5)] += C2.z;
       };
       if (type != 2) accum(acc, pos - P);
       if (type != 0) accum(acc + 21, pos - site);
@@ -832,8 +828,9 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         for (int c = tid; c < ncon; c += NT) {
           float fr, mu, a1, a2, Dn = w.cD[c];
           contact_params(w.ctype[c], fr, mu);
-          cone_ls(w.cjar[0][c] + alpha * w.cjv[0][c], w.cjar[1][c] + alpha * w.cjv[1][c], w.cjar[2][c] + alpha * w.cjv[2][c],
-                  w.cjv[0][c], w.cjv[1][c], w.cjv[2][c], Dn, Dn * dm.impratio, mu, fr, a1, a2);
+          const v3 jv = mk(w.cjv[0][c], w.cjv[1][c], w.cjv[2][c]);
+          cone_ls(mk(w.cjar[0][c], w.cjar[1][c], w.cjar[2][c]) + alpha * jv, jv, mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]), Dn, Dn * dm.impratio,
+                  mu, fr, a1, a2);
           d1 += a1; d2 += a2;
         }
         if (tid < 7 && w.lsign[lane] != 0.f) {
