@@ -24,9 +24,15 @@
 #define NPAIR_MAX 544
 
 struct __align__(16) WS {
-  float qs[NPART_MAX];                                 // slider position (slider velocity lives in hs[13..] until the CG loop starts)
-  // Hx holds (M+E)x - rhs; during set-up `grad` accumulates rhs (= qfrc_smooth + J_eq^T D aref)
+  // ---- landing zones of the 1-D TMA bulk copies (whole HBM rows, 16-byte aligned; written back the same way) ----
+  float qrow[QPAD];                                    // qpos row: [0..6] arm, [7..9] torso position, [10..13] torso quaternion, [14+i] slider i
+  // Hx holds (M+E)x - rhs; during set-up `grad` accumulates rhs (= qfrc_smooth + J_eq^T D aref).
+  // x <- qacc_warmstart row; hs <- qvel row (slider velocity lives in hs[13..] until the CG loop starts)
   float x[QPAD], Hx[QPAD], grad[QPAD], pg[QPAD], s[QPAD], hs[QPAD];
+  float ab[ARMBUF];
+  float ts[USIM_TASK_DIM];
+  unsigned long long bar;                              // mbarrier of the load
+  // ----
   float dg[NPART_MAX], dgm[NPART_MAX];                 // dg: slider diagonal of the preconditioner, stored INVERTED; dgm: M+E diagonal w/o tendon
   float Dp[NPAIR_MAX];                                 // D of each "smooth" pair
   float cpos[3][DEV_MAXC], cn[3][DEV_MAXC], cjar[3][DEV_MAXC], cjv[3][DEV_MAXC]; // cjv holds aref until the first J*x
@@ -35,8 +41,6 @@ struct __align__(16) WS {
   short cslot[NPART_MAX];                              // first contact slot of a slider (its "owner slot"), -1 = no contact
   short cpart[DEV_MAXC];
   unsigned char ctype[DEV_MAXC], czone[DEV_MAXC];
-  float ab[ARMBUF];
-  float ts[USIM_TASK_DIM];
   float R[9], p[3], vf[6], qdarm[7];
   float Mff[36], Mfw[21], Sf[49], Pa[49], Kp[21];      // Mfw: free-body inertia, world-frame omega, packed upper triangle; Sf/Pa: 7x7 Cholesky factors
   float dv[12];
@@ -47,6 +51,41 @@ struct __align__(16) WS {
 };
 
 __device__ __forceinline__ void env_sync() { __syncwarp(); }
+
+// ---- 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP): whole state rows HBM <-> shared memory, issued by one thread ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "USIM_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra USIM_DONE;\n"
+      "bra USIM_WAIT;\n"
+      "USIM_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_load_row(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_row(void* dst_gmem, const void* src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (before a bulk store reads them)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ float wsum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -208,20 +247,32 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
   float* qv_g = qvel + (size_t)env * QPAD;
   float* wm_g = warm + (size_t)env * QPAD;
 
-  // ------------------------------------------------------------------ load
-  for (int i = tid; i < ARMBUF; i += NT) w.ab[i] = armbuf[(size_t)env * ARMBUF + i];
-  for (int i = tid; i < USIM_TASK_DIM; i += NT) w.ts[i] = ts_g[i];
-  for (int i = tid; i < QPAD; i += NT) { w.x[i] = i < nv ? wm_g[i] : 0.f; w.grad[i] = 0.f; w.pg[i] = 0.f; w.s[i] = 0.f; }
-  for (int i = tid; i < np; i += NT) {
-    w.qs[i] = qp_g[14 + i]; w.hs[13 + i] = qv_g[13 + i]; w.cslot[i] = -1;
+  // ------------------------------------------------------------------ load: five TMA bulk copies, one mbarrier
+  static_assert(offsetof(WS, qrow) % 16 == 0 && offsetof(WS, x) % 16 == 0 && offsetof(WS, hs) % 16 == 0 && offsetof(WS, ab) % 16 == 0 &&
+                    offsetof(WS, ts) % 16 == 0 && (QPAD * 4) % 16 == 0 && (ARMBUF * 4) % 16 == 0 && (USIM_TASK_DIM * 4) % 16 == 0,
+                "TMA bulk copies need 16-byte aligned rows");
+  if (tid == 0) mbar_init(&w.bar, 1);
+  env_sync();
+  if (tid == 0) {
+    mbar_expect_tx(&w.bar, (3 * QPAD + ARMBUF + USIM_TASK_DIM) * 4);
+    tma_load_row(w.qrow, qp_g, QPAD * 4, &w.bar);
+    tma_load_row(w.x, wm_g, QPAD * 4, &w.bar);
+    tma_load_row(w.hs, qv_g, QPAD * 4, &w.bar);
+    tma_load_row(w.ab, armbuf + (size_t)env * ARMBUF, ARMBUF * 4, &w.bar);
+    tma_load_row(w.ts, ts_g, USIM_TASK_DIM * 4, &w.bar);
   }
+  // (overlapped with the copies)
+  for (int i = tid; i < QPAD; i += NT) { w.grad[i] = 0.f; w.pg[i] = 0.f; w.s[i] = 0.f; }
+  for (int i = tid; i < np; i += NT) w.cslot[i] = -1;
   for (int i = tid; i < 49; i += NT) w.Sf[i] = (i % 8 == 0) ? 1.f : 0.f; // identity: row/col 6 of the padded 6x6 stay like this
-  if (tid < 7) w.qdarm[tid] = qv_g[tid];
+  mbar_wait(&w.bar, 0);
+  for (int i = nv + tid; i < QPAD; i += NT) w.x[i] = 0.f; // the solver vectors are zero beyond nv
+  if (tid < 7) w.qdarm[tid] = w.hs[tid];
   float quat[4] = {1, 0, 0, 0};
   if (dm.soft) {
-    if (tid < 6) w.vf[tid] = qv_g[7 + tid];
-    if (tid < 3) w.p[tid] = qp_g[7 + tid];
-    quat[0] = qp_g[10]; quat[1] = qp_g[11]; quat[2] = qp_g[12]; quat[3] = qp_g[13];
+    if (tid < 6) w.vf[tid] = w.hs[7 + tid];
+    if (tid < 3) w.p[tid] = w.qrow[7 + tid];
+    quat[0] = w.qrow[10]; quat[1] = w.qrow[11]; quat[2] = w.qrow[12]; quat[3] = w.qrow[13];
     float nq = rsqrtf(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3]);
     quat[0] *= nq; quat[1] *= nq; quat[2] *= nq; quat[3] *= nq;
     if (tid == 0) quat2mat(quat, w.R);
@@ -251,7 +302,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     for (int i = tid; i < np; i += NT) {
       const float4 a4 = pt.ax4[i];
       v3 ah = xyz(a4), r0 = xyz(pt.ps4[i]);
-      float q = w.qs[i], sd = w.hs[13 + i], xi = w.x[13 + i];
+      float q = w.qrow[14 + i], sd = w.hs[13 + i], xi = w.x[13 + i];
       v3 c = r0 + (q - off) * ah;
       a[0] += mp * c.x; a[1] += mp * c.y; a[2] += mp * c.z;
       float cc = dot(c, c);
@@ -322,7 +373,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     for (int pr = tid; pr < dm.npair; pr += NT) {
       const int2 pr2 = eq_pairs[pr];
       const int ia = pr2.x, ib = pr2.y;
-      float pos = w.qs[ia] - w.qs[ib], vel = w.hs[13 + ia] - w.hs[13 + ib], K2, B2, imp2;
+      float pos = w.qrow[14 + ia] - w.qrow[14 + ib], vel = w.hs[13 + ia] - w.hs[13 + ib], K2, B2, imp2;
       kbi(ksm, bsm, pos, &K2, &B2, &imp2);
       float D = 1.f / fmaxf(1e-15f, (1.f - imp2) / imp2 * (pt.ax4[ia].w + pt.ax4[ib].w));
       w.Dp[pr] = D;
@@ -341,7 +392,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
   if (tid < 7) {
     w.grad[lane] = w.ab[AB_QS + lane];
     // joint limits (margin 0)
-    float q = qp_g[lane], lo = dm.jnt_lo[lane], hi = dm.jnt_hi[lane], dist = 0.f, sg = 0.f;
+    float q = w.qrow[lane], lo = dm.jnt_lo[lane], hi = dm.jnt_hi[lane], dist = 0.f, sg = 0.f;
     if (q - lo < 0.f) { dist = q - lo; sg = 1.f; } else if (hi - q < 0.f) { dist = hi - q; sg = -1.f; }
     float K, B, imp;
     kbi(dm.solref[0], dm.solref[1], dist, &K, &B, &imp);
@@ -381,7 +432,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         float d0 = 0.f, d1 = 0.f;
         if (i < np) {
           v3 ah = xyz(pt.ax4[i]), r0 = xyz(pt.ps4[i]);
-          float q = w.qs[i];
+          float q = w.qrow[14 + i];
           v3 eo = P + mv(R, r0 + (q - dm.cap_r) * ah), ei = P + mv(R, r0 + (q - dm.cap_r - 2.f * dm.cap_hl) * ah);
           if (pass == 0) {
             d0 = eo.z - dm.cap_r - dm.table_z;
@@ -752,7 +803,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         int cs = w.cslot[i];
         if (cs >= 0) {
           v3 kk = mk(w.sk[0][cs], w.sk[1][cs], w.sk[2][cs]);
-          v3 cr = mv(R, xyz(pt.ps4[i]) + (w.qs[i] - dm.cap_r) * ah);
+          v3 cr = mv(R, xyz(pt.ps4[i]) + (w.qrow[14 + i] - dm.cap_r) * ah);
           v3 ck = cross(cr, kk);
           w.sc[0][cs] = ck.x; w.sc[1][cs] = ck.y; w.sc[2][cs] = ck.z;
           bv = bv + kk;
@@ -933,28 +984,38 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       }
     }
     env_sync();
-    for (int i = tid; i < nv; i += NT) wm_g[i] = w.x[i];
-    if (tid < 7) { qv_g[tid] = w.qdarm[tid]; qp_g[lane] += h * w.qdarm[tid]; }
+    // new state rows are assembled in shared memory (qrow, hs <- qvel, x = qacc_warmstart) and leave as three TMA bulk stores
+    if (tid < 7) { w.hs[tid] = w.qdarm[tid]; w.qrow[lane] += h * w.qdarm[tid]; }
+    for (int i = 13 + np + tid; i < QPAD; i += NT) w.hs[i] = 0.f;
     if (dm.soft) {
       for (int i = tid; i < np; i += NT) {
         float v = qv_g[13 + i] + h * w.x[13 + i];
-        qv_g[13 + i] = v;
-        qp_g[14 + i] = w.qs[i] + h * v;
+        w.hs[13 + i] = v;
+        w.qrow[14 + i] += h * v;
       }
       if (tid == 0) {
         v3 vn = vlin + h * ld3(w.x + 7), wn = wl + h * ld3(w.x + 10);
-        st3(qv_g + 7, vn); st3(qv_g + 10, wn);
-        st3(qp_g + 7, P + h * vn);
+        st3(w.hs + 7, vn); st3(w.hs + 10, wn);
+        st3(w.qrow + 7, P + h * vn);
         float wnm = norm(wn), ang = h * wnm;
         if (ang > 0.f) {
           float s = sinf(0.5f * ang) / wnm, qr[4] = {cosf(0.5f * ang), s * wn.x, s * wn.y, s * wn.z}, qn[4];
           quatmul(quat, qr, qn);
           float nq = rsqrtf(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
-          qp_g[10] = qn[0] * nq; qp_g[11] = qn[1] * nq; qp_g[12] = qn[2] * nq; qp_g[13] = qn[3] * nq;
+          w.qrow[10] = qn[0] * nq; w.qrow[11] = qn[1] * nq; w.qrow[12] = qn[2] * nq; w.qrow[13] = qn[3] * nq;
         } else {
-          qp_g[10] = quat[0]; qp_g[11] = quat[1]; qp_g[12] = quat[2]; qp_g[13] = quat[3];
+          w.qrow[10] = quat[0]; w.qrow[11] = quat[1]; w.qrow[12] = quat[2]; w.qrow[13] = quat[3];
         }
       }
+    } else if (tid >= 7 && tid < 13) {
+      w.hs[tid] = 0.f;
+    }
+    fence_async_smem();
+    env_sync();
+    if (tid == 0) {
+      tma_store_row(qp_g, w.qrow, QPAD * 4);
+      tma_store_row(qv_g, w.hs, QPAD * 4);
+      tma_store_row(wm_g, w.x, QPAD * 4);
     }
   }
   env_sync();
@@ -1020,7 +1081,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         int term = 0;
 #pragma unroll
         for (int j = 0; j < 7; j++) {
-          float qn = qp_g[j];
+          float qn = w.qrow[j];
           if (!(dm.jnt_lo[j] + 0.1f < qn && qn < dm.jnt_hi[j] - 0.1f)) term = 1;
         }
         if (sqrtf(pe[0] * pe[0] + pe[1] * pe[1]) > 1.0f) term = 1;
@@ -1062,5 +1123,11 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     }
   }
   env_sync();
-  for (int i = tid; i < USIM_TASK_DIM; i += NT) ts_g[i] = w.ts[i];
+  // task record back to HBM, then wait until the bulk stores have finished READING shared memory (the CTA may not exit before)
+  fence_async_smem();
+  env_sync();
+  if (tid == 0) {
+    tma_store_row(ts_g, w.ts, USIM_TASK_DIM * 4);
+    tma_store_commit_wait();
+  }
 }
