@@ -54,7 +54,8 @@ struct DevModel {
 struct PartTables {
   const float4* ax4; // [npart] slider axis (torso frame) xyz, w = dof_invweight0 of the slider
   const float4* ps4; // [npart] rest position (torso frame) xyz, w = body_invweight0 (translational)
-  const int4* nb4;   // [npart] up to 4 grid neighbours, packed (pair << 16) | neighbour; empty slots = (npair << 16) | self
+  const int4* nb4;   // [npart] up to 4 grid neighbours, packed (pair << 16) | (second << 15) | neighbour (second: this slider is the
+                     // pair's second element, its row enters with a minus sign); empty slots = (npair << 16) | self
 };
 
 __constant__ DevModel dm;  // single translation unit (usim.cu)

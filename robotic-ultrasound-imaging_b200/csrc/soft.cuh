@@ -19,8 +19,14 @@
 #pragma once
 #include "common.cuh"
 
-// One env per CTA of one warp: no CTA waits for a slower env (measured 1/2/4/8 envs per CTA: 2.17/2.12/1.96/1.82 M steps/s).
-#define NT 32
+// One env per CTA: no CTA waits for a slower env (measured 1/2/4/8 envs per CTA: 2.17/2.12/1.96/1.82 M steps/s).
+// WPE warps cooperate on that env over the same shared-memory image: twice the resident warps per SM for the same shared memory,
+// half the latency of one env (a 4096-env launch is only ~3.5 waves of CTAs: the tail matters), one instruction stream fetched for two warps.
+// Every cross-lane / cross-warp accumulation has a fixed association order: results are bit-reproducible for a given WPE.
+#ifndef WPE
+#define WPE 2
+#endif
+#define NT (32 * WPE)
 #define NPAIR_MAX 544
 
 struct __align__(16) WS {
@@ -36,21 +42,37 @@ struct __align__(16) WS {
   float dg[NPART_MAX], dgm[NPART_MAX];                 // dg: slider diagonal of the preconditioner, stored INVERTED; dgm: M+E diagonal w/o tendon
   float Dp[NPAIR_MAX];                                 // D of each "smooth" pair
   float cpos[3][DEV_MAXC], cn[3][DEV_MAXC], cjar[3][DEV_MAXC], cjv[3][DEV_MAXC]; // cjv holds aref until the first J*x
-  float cD[DEV_MAXC], cdist[DEV_MAXC];
+  float cD[DEV_MAXC];
+  float cfs[DEV_MAXC];                                 // per-contact scratch: penetration depth until K5, then the contact's share of a slider row
   float sk[3][DEV_MAXC], sc[3][DEV_MAXC];              // per owner slot of a slider with contacts: K a (world), lever x K a
   short cslot[NPART_MAX];                              // first contact slot of a slider (its "owner slot"), -1 = no contact
+  short cslot2[NPART_MAX];                             // slot of the slider's probe contact, -1 = none
   short cpart[DEV_MAXC];
   unsigned char ctype[DEV_MAXC], czone[DEV_MAXC];
   float R[9], p[3], vf[6], qdarm[7];
-  float Mff[36], Mfw[21], Sf[49], Pa[49], Kp[21];      // Mfw: free-body inertia, world-frame omega, packed upper triangle; Sf/Pa: 7x7 Cholesky factors
+  float Mff[36], Mfw[21], Sf[49], Pa[49];              // Mfw: free-body inertia, world-frame omega, packed upper triangle; Sf/Pa: 7x7 Cholesky factors
   float dv[12];
-  float r3[24], rg[16], rp[16], rq[8], rl[4];          // landing zones of the warp reductions (one per call site)
+  // landing zones of the warp reductions, one per call site, one row per warp (readers add the rows in a fixed order: rd())
+  float r3[WPE][24], rg[WPE][16], rp[WPE][16], rq[WPE][8], rl[2][WPE][4], rb1[WPE][24], rb2[WPE][24], rb3[WPE][24];
   float lsign[7], lD[7], laref[7];
   float Dt, areft;
-  int ncon;
+  int ncon, okf;
+  int cnt[2][WPE];                                     // cross-warp prefix of the contact compaction (double buffered)
 };
+static_assert(sizeof(WS) + 1024 <= 233472 / 8, "WS must leave room for 8 CTAs per SM");
+static_assert(2 * QPAD >= NPAIR_MAX + 1, "pg|s double as the pair scratch of K3");
 
-__device__ __forceinline__ void env_sync() { __syncwarp(); }
+__device__ __forceinline__ void env_sync() {
+  if (WPE == 1) __syncwarp(); else __syncthreads();
+}
+// total of entry k of a reduction landing zone (rows = warps, added in warp order)
+template <int N>
+__device__ __forceinline__ float rd(const float (*z)[N], int k) {
+  float t = z[0][k];
+#pragma unroll
+  for (int q = 1; q < WPE; q++) t += z[q][k];
+  return t;
+}
 
 // ---- 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP): whole state rows HBM <-> shared memory, issued by one thread ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -233,7 +255,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     float* __restrict__ diag, int* __restrict__ ncon_out, int* __restrict__ geom1_out, int* __restrict__ geom2_out,
     float* __restrict__ dist_out, int* __restrict__ diverged) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int env = blockIdx.x;
   if (env >= n) return;
   if (mask && !mask[env]) return;
@@ -263,7 +285,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
   }
   // (overlapped with the copies)
   for (int i = tid; i < QPAD; i += NT) { w.grad[i] = 0.f; w.pg[i] = 0.f; w.s[i] = 0.f; }
-  for (int i = tid; i < np; i += NT) w.cslot[i] = -1;
+  for (int i = tid; i < np; i += NT) { w.cslot[i] = -1; w.cslot2[i] = -1; }
   for (int i = tid; i < 49; i += NT) w.Sf[i] = (i % 8 == 0) ? 1.f : 0.f; // identity: row/col 6 of the padded 6x6 stay like this
   mbar_wait(&w.bar, 0);
   for (int i = nv + tid; i < QPAD; i += NT) w.x[i] = 0.f; // the solver vectors are zero beyond nv
@@ -321,23 +343,26 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       w.dgm[i] = mp + D;
       w.grad[13 + i] = -dot(ah, F) + D * (-B * sd - K * imp * q);
     }
-    tsum_to(a, lane, w.r3);
+    tsum_to(a, lane, w.r3[wrp]);
     env_sync();
     // tendon equality: sum q = 0
-    const float a_q = w.r3[15], a_v = w.r3[16];
-    S4[0] = w.r3[17]; S4[1] = w.r3[18]; S4[2] = w.r3[19]; S4[3] = w.r3[20];
+    const float a_q = rd(w.r3, 15), a_v = rd(w.r3, 16);
+    S4[0] = rd(w.r3, 17); S4[1] = rd(w.r3, 18); S4[2] = rd(w.r3, 19); S4[3] = rd(w.r3, 20);
     float K, B, imp;
     kbi(dm.solref[0], dm.solref[1], a_q, &K, &B, &imp);
     const float Dt = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * dm.tendon_iw);
     const float areft = -B * a_v - K * imp * a_q;
     if (tid == 0) {
       const float mtot = np * mp + dm.center_mass;
-      const v3 mc = ld3(w.r3);
+      float t15[15];
+#pragma unroll
+      for (int k = 0; k < 15; k++) t15[k] = rd(w.r3, k);
+      const v3 mc = ld3(t15);
       w.Dt = Dt; w.areft = areft;
       // M_ff: [v (world); omega (body)]
       // rotational inertia: parallel-axis part (depends on q) + constant part (capsules about their COM, centre geom)
-      float It[9] = {w.r3[9] + dm.rot_I[0],  w.r3[12] + dm.rot_I[3], w.r3[13] + dm.rot_I[4], w.r3[12] + dm.rot_I[3], w.r3[10] + dm.rot_I[1],
-                     w.r3[14] + dm.rot_I[5], w.r3[13] + dm.rot_I[4], w.r3[14] + dm.rot_I[5], w.r3[11] + dm.rot_I[2]};
+      float It[9] = {t15[9] + dm.rot_I[0],  t15[12] + dm.rot_I[3], t15[13] + dm.rot_I[4], t15[12] + dm.rot_I[3], t15[10] + dm.rot_I[1],
+                     t15[14] + dm.rot_I[5], t15[13] + dm.rot_I[4], t15[14] + dm.rot_I[5], t15[11] + dm.rot_I[2]};
       for (int k = 0; k < 36; k++) w.Mff[k] = 0.f;
       for (int k = 0; k < 3; k++) w.Mff[k * 6 + k] = mtot;
       // M_v,omega = -R [mc]x  ;  [mc]x = [[0,-z,y],[z,0,-x],[-y,x,0]]
@@ -361,7 +386,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         M[tri6(3, 3)] = Iw[0]; M[tri6(3, 4)] = Iw[1]; M[tri6(3, 5)] = Iw[2]; M[tri6(4, 4)] = Iw[4]; M[tri6(4, 5)] = Iw[5]; M[tri6(5, 5)] = Iw[8];
       }
       // bias of the free body
-      v3 sF = ld3(w.r3 + 3), sT = ld3(w.r3 + 6);
+      v3 sF = ld3(t15 + 3), sT = ld3(t15 + 6);
       v3 bv = mv(R, sF) - dm.center_mass * ld3(dm.g);
       v3 Iw = symv(dm.rot_I, wl);
       v3 bw = sT + cross(wl, Iw);
@@ -369,7 +394,8 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       w.grad[10] = -bw.x - dm.free_damp * wl.x; w.grad[11] = -bw.y - dm.free_damp * wl.y; w.grad[12] = -bw.z - dm.free_damp * wl.z;
     }
     env_sync();
-    // "smooth" pair equalities (carry solrefsmooth = (-stiffness, -damping) of this episode)
+    // "smooth" pair equalities (carry solrefsmooth = (-stiffness, -damping) of this episode); scratch: pg|s (contiguous, unused so far)
+    float* arp = w.pg;
     for (int pr = tid; pr < dm.npair; pr += NT) {
       const int2 pr2 = eq_pairs[pr];
       const int ia = pr2.x, ib = pr2.y;
@@ -377,17 +403,21 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       kbi(ksm, bsm, pos, &K2, &B2, &imp2);
       float D = 1.f / fmaxf(1e-15f, (1.f - imp2) / imp2 * (pt.ax4[ia].w + pt.ax4[ib].w));
       w.Dp[pr] = D;
-      if (pr == 0) w.Dp[dm.npair] = 0.f; // the slot empty neighbour entries point at
-      float ar = D * (-B2 * vel - K2 * imp2 * pos);
-      atomicAdd(&w.grad[13 + ia], ar); atomicAdd(&w.grad[13 + ib], -ar);
+      arp[pr] = D * (-B2 * vel - K2 * imp2 * pos); // D aref of the pair row: + on its first slider, - on its second
+      if (pr == 0) { w.Dp[dm.npair] = 0.f; arp[dm.npair] = 0.f; } // the slot empty neighbour entries point at
     }
     env_sync();
+    // every slider gathers its (at most 4) pair rows in table order: no atomics, the same sum in any thread arrangement
     for (int i = tid; i < np; i += NT) {
       const int4 e = pt.nb4[i];
       float sd = w.Dp[e.x >> 16] + w.Dp[e.y >> 16] + w.Dp[e.z >> 16] + w.Dp[e.w >> 16];
-      w.grad[13 + i] += Dt * areft;
+      float sa = ((e.x & 0x8000) ? -arp[e.x >> 16] : arp[e.x >> 16]) + ((e.y & 0x8000) ? -arp[e.y >> 16] : arp[e.y >> 16]) +
+                 ((e.z & 0x8000) ? -arp[e.z >> 16] : arp[e.z >> 16]) + ((e.w & 0x8000) ? -arp[e.w >> 16] : arp[e.w >> 16]);
+      w.grad[13 + i] += Dt * areft + sa;
       w.dgm[i] += sd;
     }
+    env_sync();
+    for (int i = tid; i < 2 * QPAD; i += NT) arp[i] = 0.f; // pg and s start the solve as zero vectors
   }
   if (tid < 7) {
     w.grad[lane] = w.ab[AB_QS + lane];
@@ -412,7 +442,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         if (dist < 0.f && fabsf(ends[e].x) <= dm.table_half && fabsf(ends[e].y) <= dm.table_half) {
           w.cpos[0][ncon] = ends[e].x; w.cpos[1][ncon] = ends[e].y; w.cpos[2][ncon] = dm.table_z + 0.5f * dist;
           w.cn[0][ncon] = 0.f; w.cn[1][ncon] = 0.f; w.cn[2][ncon] = 1.f;
-          w.cdist[ncon] = dist; w.cpart[ncon] = -1; w.ctype[ncon] = 2;
+          w.cfs[ncon] = dist; w.cpart[ncon] = -1; w.ctype[ncon] = 2;
           ncon++;
         }
       }
@@ -423,6 +453,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
   }
   if (dm.soft) {
     const unsigned lt = (1u << lane) - 1u;
+    int cphase = 0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) { // pass 0: (table, particle k); pass 1: (probe, particle k)
       for (int base = 0; base < np; base += NT) {
@@ -453,20 +484,30 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
           }
         }
         unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
-        int total = __popc(b0) + __popc(b1);
-        int slot = ncon + __popc(b0 & lt) + __popc(b1 & lt);
+        int before = 0, total = __popc(b0) + __popc(b1);
+        if (WPE > 1) { // cross-warp exclusive prefix of the per-warp hit counts (keeps the particle order)
+          int* cb = w.cnt[cphase];
+          cphase ^= 1;
+          if (lane == 0) cb[wrp] = total;
+          __syncthreads();
+          total = 0;
+#pragma unroll
+          for (int q = 0; q < WPE; q++) { if (q < wrp) before += cb[q]; total += cb[q]; }
+        }
+        int slot = ncon + before + __popc(b0 & lt) + __popc(b1 & lt);
         // owner slot of the slider: its first contact (the same thread handles slider i in both passes)
         if ((h0 || h1) && slot < DEV_MAXC && w.cslot[i] < 0) w.cslot[i] = (short)slot;
+        if (pass == 1 && h0 && slot < DEV_MAXC) w.cslot2[i] = (short)slot;
         if (h0 && slot < DEV_MAXC) {
           w.cpos[0][slot] = p0.x; w.cpos[1][slot] = p0.y; w.cpos[2][slot] = p0.z;
           w.cn[0][slot] = n0.x; w.cn[1][slot] = n0.y; w.cn[2][slot] = n0.z;
-          w.cdist[slot] = d0; w.cpart[slot] = (short)i; w.ctype[slot] = (unsigned char)pass;
+          w.cfs[slot] = d0; w.cpart[slot] = (short)i; w.ctype[slot] = (unsigned char)pass;
         }
         if (h0) slot++;
         if (h1 && slot < DEV_MAXC) {
           w.cpos[0][slot] = p1.x; w.cpos[1][slot] = p1.y; w.cpos[2][slot] = p1.z;
           w.cn[0][slot] = 0.f; w.cn[1][slot] = 0.f; w.cn[2][slot] = -1.f;
-          w.cdist[slot] = d1; w.cpart[slot] = (short)i; w.ctype[slot] = 0;
+          w.cfs[slot] = d1; w.cpart[slot] = (short)i; w.ctype[slot] = 0;
         }
         ncon += total;
       }
@@ -501,12 +542,13 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     }
     if (type != 0) { rel = rel + Vs + cross(Ws, pos - site); diagA += dm.iw_probe; }
     float K, B, imp;
-    kbi(dm.solref[0], dm.solref[1], w.cdist[c], &K, &B, &imp);
+    kbi(dm.solref[0], dm.solref[1], w.cfs[c], &K, &B, &imp);
     w.cD[c] = 1.f / fmaxf(1e-15f, (1.f - imp) / imp * diagA);
     // aref = -B v_rel - K imp dist n: the normal row carries the position term, the tangential rows only damping
-    v3 ar = (-B) * rel - (K * imp * w.cdist[c]) * nn;
+    v3 ar = (-B) * rel - (K * imp * w.cfs[c]) * nn;
     w.cjv[0][c] = ar.x; w.cjv[1][c] = ar.y; w.cjv[2][c] = ar.z;
     w.czone[c] = 255; // "unknown": the first gradient evaluation always reports a change
+    if (dist_out) dist_out[(size_t)env * DEV_MAXC + c] = w.cfs[c]; // the depth leaves here: cfs becomes scratch
   }
   env_sync();
 
@@ -523,8 +565,8 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         // 4 packed (pair << 16 | neighbour) entries in one 16-byte load, no data-dependent branch
         const int4 e = pt.nb4[i];
         float acc = mp * dot(ah, ivl) + w.dgm[i] * xi + dts;
-        acc -= w.Dp[e.x >> 16] * in[13 + (e.x & 0xffff)]; acc -= w.Dp[e.y >> 16] * in[13 + (e.y & 0xffff)];
-        acc -= w.Dp[e.z >> 16] * in[13 + (e.z & 0xffff)]; acc -= w.Dp[e.w >> 16] * in[13 + (e.w & 0xffff)];
+        acc -= w.Dp[e.x >> 16] * in[13 + (e.x & 0x7fff)]; acc -= w.Dp[e.y >> 16] * in[13 + (e.y & 0x7fff)];
+        acc -= w.Dp[e.z >> 16] * in[13 + (e.z & 0x7fff)]; acc -= w.Dp[e.w >> 16] * in[13 + (e.w & 0x7fff)];
         out[13 + i] = acc;
         if (q) { q[0] += xi * w.Hx[13 + i]; q[1] += xi * acc; }
       }
@@ -546,16 +588,18 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       }
     }
     // dv[0..5] = Jsite in_arm ; dv[6..8] = in_v ; dv[9..11] = R in_omega
-    if (tid >= 16 && tid < 22) {
-      int r = lane - 16;
+    // (done by the LAST warp of the env: the dense rows above belong to the first)
+    const int dl = tid - (NT - 16);
+    if (dl >= 0 && dl < 6) {
+      int r = dl;
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 7; j++) s += w.ab[AB_JSITE + r * 7 + j] * in[j];
       w.dv[r] = s;
-    } else if (tid >= 22 && tid < 25) {
-      w.dv[6 + lane - 22] = dm.soft ? in[7 + lane - 22] : 0.f;
-    } else if (tid >= 25 && tid < 28) {
-      int r = lane - 25;
+    } else if (dl >= 6 && dl < 9) {
+      w.dv[dl] = dm.soft ? in[7 + dl - 6] : 0.f;
+    } else if (dl >= 9 && dl < 12) {
+      int r = dl - 9;
       w.dv[9 + r] = dm.soft ? w.R[3 * r] * in[10] + w.R[3 * r + 1] * in[11] + w.R[3 * r + 2] * in[12] : 0.f;
     }
     env_sync();
@@ -575,6 +619,15 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     }
     env_sync();
   };
+  // sum of a per-contact quantity over the contacts of slider i, called by its owner slot c: the second table contact sits in
+  // the next slot, the probe contact (if any, and if it is not the owner itself) in cslot2
+  auto slider_gather = [&](const float* v, int c, int i) -> float {
+    float f = v[c];
+    if (w.ctype[c] == 0 && c + 1 < ncon && w.cpart[c + 1] == i && w.ctype[c + 1] == 0) f += v[c + 1];
+    const int c2 = w.cslot2[i];
+    if (c2 >= 0 && c2 != c) f += v[c2];
+    return f;
+  };
   // grad (= Hx on entry) -= J^T f(jar).  Lands in w.rg: [0..5] torso wrench about P, [6..11] probe wrench about the site,
   // [12] zone changes, [13] hx2, [14] rhs2 (the caller's two riders).
   auto update_grad = [&](float hx2, float rhs2) {
@@ -590,24 +643,30 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       const v3 Fw = cone_force(mk(w.cjar[0][c], w.cjar[1][c], w.cjar[2][c]), nn, Dn, Dn * dm.impratio, mu, fr, zone); // force on geom2
       if (zone != (int)w.czone[c]) g[12] += 1.f;
       w.czone[c] = (unsigned char)zone;
+      w.cfs[c] = 0.f;
       if (zone == 0) continue;
       const v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]);
       if (type != 2) {
         v3 Fp = -Fw, T = cross(pos - P, Fp);
         g[0] += Fp.x; g[1] += Fp.y; g[2] += Fp.z; g[3] += T.x; g[4] += T.y; g[5] += T.z;
-        atomicAdd(&w.grad[13 + i], -dot(mv(R, xyz(pt.ax4[i])), Fp));
+        w.cfs[c] = -dot(mv(R, xyz(pt.ax4[i])), Fp); // this contact's share of its slider's row, gathered by the owner below
       }
       if (type != 0) {
         v3 T = cross(pos - site, Fw);
         g[6] += Fw.x; g[7] += Fw.y; g[8] += Fw.z; g[9] += T.x; g[10] += T.y; g[11] += T.z;
       }
     }
-    tsum_to(g, lane, w.rg);
+    tsum_to(g, lane, w.rg[wrp]);
     env_sync();
+    // slider rows: the owner contact of each slider adds the shares of its (at most 3) contacts in slot order -- no atomics
+    for (int c = tid; c < ncon; c += NT) {
+      const int i = w.cpart[c];
+      if (i >= 0 && w.cslot[i] == c) w.grad[13 + i] += slider_gather(w.cfs, c, i);
+    }
     if (tid < 7) {
       float s = 0.f;
 #pragma unroll
-      for (int r = 0; r < 6; r++) s += w.ab[AB_JSITE + r * 7 + lane] * w.rg[6 + r];
+      for (int r = 0; r < 6; r++) s += w.ab[AB_JSITE + r * 7 + lane] * rd(w.rg, 6 + r);
       // joint limit row
       float sg = w.lsign[lane];
       if (sg != 0.f) {
@@ -616,10 +675,10 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       }
       w.grad[lane] -= s;
     } else if (tid < 10 && dm.soft) {
-      w.grad[lane] -= w.rg[lane - 7];
+      w.grad[lane] -= rd(w.rg, lane - 7);
     } else if (tid < 13 && dm.soft) {
       int r = lane - 10; // R^T torque
-      w.grad[lane] -= w.R[r] * w.rg[3] + w.R[3 + r] * w.rg[4] + w.R[6 + r] * w.rg[5];
+      w.grad[lane] -= w.R[r] * rd(w.rg, 3) + w.R[3 + r] * rd(w.rg, 4) + w.R[6 + r] * rd(w.rg, 5);
     }
     env_sync();
   };
@@ -643,7 +702,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       }
     }
     if (tid < 13) a[9] += w.grad[lane] * w.pg[lane];
-    tsum_to(a, lane, w.rp);
+    tsum_to(a, lane, w.rp[wrp]);
     env_sync();
     float gd[13]; // dense part of the gradient
 #pragma unroll
@@ -655,7 +714,10 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
     float y[6] = {0, 0, 0, 0, 0, 0};
     v3 yl = mk(0, 0, 0), yb = mk(0, 0, 0);
     if (dm.soft) {
-      v3 tv = mp * mv(R, ld3(w.rp)) + ld3(w.rp + 3), gw = mv(R, mk(gd[10], gd[11], gd[12])) - ld3(w.rp + 6);
+      float t9[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) t9[k] = rd(w.rp, k);
+      v3 tv = mp * mv(R, ld3(t9)) + ld3(t9 + 3), gw = mv(R, mk(gd[10], gd[11], gd[12])) - ld3(t9 + 6);
       y[0] = gd[7] - tv.x; y[1] = gd[8] - tv.y; y[2] = gd[9] - tv.z; y[3] = gw.x; y[4] = gw.y; y[5] = gw.z;
       chol7_solve<6>(w.Sf, y);
       yl = mtv(R, mk(y[0], y[1], y[2]));
@@ -681,14 +743,14 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         by += w.sk[0][cs] * y[0] + w.sk[1][cs] * y[1] + w.sk[2][cs] * y[2] + w.sc[0][cs] * y[3] + w.sc[1][cs] * y[4] + w.sc[2][cs] * y[5];
       // slider block D - W (W: the pair couplings) inverted to second order, D^-1 + D^-1 W D^-1: hs holds D^-1 grad
       const int4 e = pt.nb4[i];
-      float nb = w.Dp[e.x >> 16] * w.hs[13 + (e.x & 0xffff)] + w.Dp[e.y >> 16] * w.hs[13 + (e.y & 0xffff)] +
-                 w.Dp[e.z >> 16] * w.hs[13 + (e.z & 0xffff)] + w.Dp[e.w >> 16] * w.hs[13 + (e.w & 0xffff)];
+      float nb = w.Dp[e.x >> 16] * w.hs[13 + (e.x & 0x7fff)] + w.Dp[e.y >> 16] * w.hs[13 + (e.y & 0x7fff)] +
+                 w.Dp[e.z >> 16] * w.hs[13 + (e.z & 0x7fff)] + w.Dp[e.w >> 16] * w.hs[13 + (e.w & 0x7fff)];
       float p = w.hs[13 + i] + (nb - by) * w.dg[i];
       w.pg[13 + i] = p;
       b[0] += g * p; b[1] += g * g; b[2] += p;
       b[3] += mp * ah.x * p; b[4] += mp * ah.y * p; b[5] += mp * ah.z * p;
     }
-    tsum_to(b, lane, w.rq);
+    tsum_to(b, lane, w.rq[wrp]);
     env_sync();
   };
 
@@ -696,17 +758,13 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
   auto build_precond = [&]() {
 #pragma unroll 1
     for (int i = tid; i < np; i += NT) w.dg[i] = w.dgm[i] + w.Dt;
-#pragma unroll 1
-    for (int c = tid; c < ncon; c += NT) {
-      w.sk[0][c] = 0.f; w.sk[1][c] = 0.f; w.sk[2][c] = 0.f; w.sc[0][c] = 0.f; w.sc[1][c] = 0.f; w.sc[2][c] = 0.f;
-    }
-    env_sync();
     float acc[42]; // packed upper triangles of the 6x6 wrench-space Hessians: [0..20] torso side (about P), [21..41] probe side (about the site)
 #pragma unroll
     for (int k = 0; k < 42; k++) acc[k] = 0.f;
 #pragma unroll 1
     for (int c = tid; c < ncon; c += NT) {
       int zone = w.czone[c], type = w.ctype[c], i = w.cpart[c];
+      w.sc[0][c] = 0.f; w.sc[1][c] = 0.f; w.sc[2][c] = 0.f; w.cfs[c] = 0.f; // this contact's share of its slider's (K a, a^T K a)
       if (zone == 0) continue;
       const float Dn = w.cD[c], Dtn = Dn * dm.impratio;
       const v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]);
@@ -736,12 +794,11 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       Ks[4] = cnn * nn.y * nn.z + cu * u.y * u.z + cg * gv.y * gv.z;
       Ks[5] = ci + cnn * nn.z * nn.z + cu * u.z * u.z + cg * gv.z * gv.z;
       const v3 K0 = mk(Ks[0], Ks[1], Ks[2]), K1 = mk(Ks[1], Ks[3], Ks[4]), K2 = mk(Ks[2], Ks[4], Ks[5]);
-      if (type != 2) { // slider of this particle: (K a_i) into its owner slot, a_i^T K a_i onto its diagonal
+      if (type != 2) { // slider of this particle: K a_i and a_i^T K a_i, gathered per slider by its owner slot below
         v3 aw = mv(R, xyz(pt.ax4[i]));
         v3 ka = mk(dot(K0, aw), dot(K1, aw), dot(K2, aw));
-        int own = w.cslot[i];
-        atomicAdd(&w.sk[0][own], ka.x); atomicAdd(&w.sk[1][own], ka.y); atomicAdd(&w.sk[2][own], ka.z);
-        atomicAdd(&w.dg[i], dot(aw, ka));
+        w.sc[0][c] = ka.x; w.sc[1][c] = ka.y; w.sc[2][c] = ka.z;
+        w.cfs[c] = dot(aw, ka);
       }
       // wrench-space Hessian [I; [r]x] K [I, [r]x^T] (force; torque about the reference point), packed upper triangle:
       // upper-right block rows r x K_i, lower-right block columns r x (column of the upper-right block)
@@ -757,15 +814,24 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       if (type != 2) accum(acc, pos - P);
       if (type != 0) accum(acc + 21, pos - site);
     }
-    // entry l of each packed triangle lands in lane l
-    float kf, kp;
+    // entry l of each packed triangle lands in lane l of every warp, then in row `wrp` of rb1 / rb2
     {
       float(&lo21)[21] = *reinterpret_cast<float(*)[21]>(acc);
       float(&hi21)[21] = *reinterpret_cast<float(*)[21]>(acc + 21);
-      kf = tsum(lo21, lane);
-      kp = tsum(hi21, lane);
+      tsum_to(lo21, lane, w.rb1[wrp]);
+      tsum_to(hi21, lane, w.rb2[wrp]);
     }
-    if (lane < 21) w.Kp[lane] = kp;
+    env_sync();
+    const float kf = lane < 21 ? rd(w.rb1, lane) : 0.f;
+    // owner slots: sk <- sum of the slider's K a, diagonal += sum of a^T K a (fixed slot order, no atomics)
+#pragma unroll 1
+    for (int c = tid; c < ncon; c += NT) {
+      const int i = w.cpart[c];
+      if (i >= 0 && w.cslot[i] == c) {
+        w.sk[0][c] = slider_gather(w.sc[0], c, i); w.sk[1][c] = slider_gather(w.sc[1], c, i); w.sk[2][c] = slider_gather(w.sc[2], c, i);
+        w.dg[i] += slider_gather(w.cfs, c, i);
+      }
+    }
     env_sync();
     // arm block: Pa = M + Jsite^T Kp Jsite + limits   (lanes 0..6, column `lane`)
     float pa_col[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -775,7 +841,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       for (int a2 = 0; a2 < 6; a2++) {
         float sacc = 0.f;
 #pragma unroll
-        for (int b2 = 0; b2 < 6; b2++) sacc += w.Kp[tri6(a2, b2)] * w.ab[AB_JSITE + b2 * 7 + lane];
+        for (int b2 = 0; b2 < 6; b2++) sacc += rd(w.rb2, tri6(a2, b2)) * w.ab[AB_JSITE + b2 * 7 + lane];
         KJ[a2] = sacc;
       }
 #pragma unroll
@@ -789,7 +855,6 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       }
     }
     // torso block (world-frame omega): Sf = Mfw + Kf - sum_i b_i b_i^T / dg_i,  b_i = [m a_i + K a_i ; r_i x K a_i]
-    float sbl = 0.f;
     if (dm.soft) {
       float sb[21];
 #pragma unroll
@@ -816,20 +881,26 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         sb[tri6(0, 0)] += bv.x * bv.x * inv; sb[tri6(0, 1)] += bv.x * bv.y * inv; sb[tri6(0, 2)] += bv.x * bv.z * inv;
         sb[tri6(1, 1)] += bv.y * bv.y * inv; sb[tri6(1, 2)] += bv.y * bv.z * inv; sb[tri6(2, 2)] += bv.z * bv.z * inv;
       }
-      sbl = tsum(sb, lane);
+      tsum_to(sb, lane, w.rb3[wrp]);
     }
     // both factorisations at once (Sf is a 6x6 padded to 7x7).  If Sf lost positive definiteness (fp32) the second attempt
     // drops the slider coupling: the free block alone is positive definite.
 #pragma unroll 1
     for (int attempt = 0; attempt < 2; attempt++) {
-      if (dm.soft && lane < 21) {
-        int ab2 = c_tri6[lane], a2 = ab2 >> 4, b2 = ab2 & 15;
-        float v = w.Mfw[lane] + kf - (attempt == 0 ? sbl : 0.f);
+      env_sync(); // rb3 (first attempt) / the restored Pa and the cleared slots (second attempt) are in place
+      if (dm.soft && tid < 21) {
+        int ab2 = c_tri6[tid], a2 = ab2 >> 4, b2 = ab2 & 15;
+        float v = w.Mfw[tid] + kf - (attempt == 0 ? rd(w.rb3, tid) : 0.f);
         w.Sf[a2 * 7 + b2] = v; w.Sf[b2 * 7 + a2] = v;
       }
       env_sync();
-      bool ok = chol7_warp2(w.Sf, w.Pa, lane);
-      if (__all_sync(0xffffffffu, ok || lane >= 8)) break;
+      if (wrp == 0) {
+        const bool ok = chol7_warp2(w.Sf, w.Pa, lane);
+        const bool allok = __all_sync(0xffffffffu, ok || lane >= 8);
+        if (lane == 0) w.okf = allok;
+      }
+      env_sync();
+      if (w.okf) break;
 #pragma unroll 1
       for (int c = tid; c < ncon; c += NT) {
         w.sk[0][c] = 0.f; w.sk[1][c] = 0.f; w.sk[2][c] = 0.f; w.sc[0][c] = 0.f; w.sc[1][c] = 0.f; w.sc[2][c] = 0.f;
@@ -840,7 +911,6 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         for (int r2 = 0; r2 < 7; r2++) w.Pa[r2 * 7 + lane] = pa_col[r2];
       }
     }
-    env_sync();
   };
 
   // ------------------------------------------------------------------ K6: nonlinear PCG; pass -1 evaluates the warm start
@@ -891,12 +961,12 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
         {
           // the quadratic part (s.Hx, s.Hs) rides on every reduction: constant cost, one call site
           float r4[4] = {d1, d2, q12[0], q12[1]};
-          tsum_to(r4, lane, w.rl);
+          float(*zl)[4] = w.rl[ls & 1]; // alternating landing zones: the next pass may start before every thread has read this one
+          tsum_to(r4, lane, zl[wrp]);
           env_sync();
-          q1 = w.rl[2]; q2 = w.rl[3];
-          d1 = w.rl[0] + q1 + alpha * q2;
-          d2 = w.rl[1] + q2;
-          env_sync(); // w.rl is rewritten by the next pass
+          q1 = rd(zl, 2); q2 = rd(zl, 3);
+          d1 = rd(zl, 0) + q1 + alpha * q2;
+          d2 = rd(zl, 1) + q2;
         }
         if (ls == 0) d0abs = fabsf(d1);
         if (fabsf(d1) <= 1e-5f * d0abs || !(d2 > 0.f)) break;
@@ -918,9 +988,9 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       env_sync();
     }
     update_grad(hx2, rhs2);
-    const bool changed = w.rg[12] > 0.f;
-    hxn = sqrtf(w.rg[13]);
-    if (init) rhsn = sqrtf(w.rg[14]);
+    const bool changed = rd(w.rg, 12) > 0.f;
+    hxn = sqrtf(rd(w.rg, 13));
+    if (init) rhsn = sqrtf(rd(w.rg, 14));
     bool restart = init;
     // soft scene: rebuild when the active set moved; rigid scene (7 unknowns): exact Hessian every iteration = Newton
     if (init || (changed && rebuilds < dm.max_rebuilds) || (!dm.soft && ncon > 0)) {
@@ -929,18 +999,18 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       restart = true;
     }
     precond();
-    const float gpo = w.rp[9], gpn = w.rq[0]; // grad.pg with the previous pg (Polak-Ribiere) and with the new one
-    gnorm = sqrtf(w.rq[1]);
+    const float gpo = rd(w.rp, 9), gpn = rd(w.rq, 0); // grad.pg with the previous pg (Polak-Ribiere) and with the new one
+    gnorm = sqrtf(rd(w.rq, 1));
     float beta = restart ? 0.f : fmaxf(0.f, (gpn - gpo) / fmaxf(gpg, 1e-30f));
     gpg = gpn;
 #pragma unroll
-    for (int k = 0; k < 4; k++) S4[k] = -w.rq[2 + k] + beta * S4[k];
+    for (int k = 0; k < 4; k++) S4[k] = -rd(w.rq, 2 + k) + beta * S4[k];
     for (int i = tid; i < nv; i += NT) w.s[i] = -w.pg[i] + beta * w.s[i];
     env_sync();
   }
 
   // ------------------------------------------------------------------ K8: probe wrench, F/T torque
-  v3 cfrc = ld3(w.rg + 6), ctq = ld3(w.rg + 9); // probe wrench of the last gradient evaluation
+  v3 cfrc = mk(rd(w.rg, 6), rd(w.rg, 7), rd(w.rg, 8)), ctq = mk(rd(w.rg, 9), rd(w.rg, 10), rd(w.rg, 11)); // probe wrench of the last gradient evaluation
   v3 ft;
   {
     float t3[3];
@@ -955,7 +1025,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
   }
   bool in_contact = false;
   for (int c = tid; c < ncon; c += NT) in_contact |= (w.ctype[c] == 1);
-  in_contact = __any_sync(0xffffffffu, in_contact);
+  in_contact = WPE == 1 ? __any_sync(0xffffffffu, in_contact) : (bool)__syncthreads_or(in_contact);
 
   // ------------------------------------------------------------------ K7: integrate (mj_Euler) and write the state back
   if (mode == 0) {
@@ -971,7 +1041,7 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       w.dv[lane] = s;
     }
     env_sync();
-    chol7_warp2(w.Pa, w.Pa, lane);
+    if (wrp == 0) chol7_warp2(w.Pa, w.Pa, lane);
     env_sync();
     {
       float b[7];
@@ -1028,14 +1098,18 @@ __global__ void __launch_bounds__(NT, 8) solve_kernel(
       if (type == 2) { g1 = 1; g2 = 2; } else { g1 = 4 + w.cpart[c]; g2 = type == 0 ? 1 : 2; }
       geom1_out[(size_t)env * DEV_MAXC + c] = g1;
       geom2_out[(size_t)env * DEV_MAXC + c] = g2;
-      if (dist_out) dist_out[(size_t)env * DEV_MAXC + c] = w.cdist[c];
     }
   }
 
   // divergence guard (MuJoCo resets on bad qacc): a non-finite solution ends the episode, the reset wipes the state
   float xnorm2 = 0.f;
-  for (int i = tid; i < nv; i += NT) xnorm2 += w.x[i] * w.x[i];
-  xnorm2 = wsum(xnorm2);
+  {
+    float x1[1] = {0.f};
+    for (int i = tid; i < nv; i += NT) x1[0] += w.x[i] * w.x[i];
+    tsum_to(x1, lane, w.rq[wrp]);
+    env_sync();
+    xnorm2 = rd(w.rq, 0);
+  }
   // ------------------------------------------------------------------ K9: task epilogue (lane 0)
   if (tid == 0) {
     float* ts = w.ts;

@@ -201,7 +201,8 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
       for (int k = 0; k < 6; k++)
         if (nbr[6 * i + k] >= 0) {
           if (cnt == 4 || nbrp[6 * i + k] < 0) { g_err = "usim_create: the composite's pair stencil has more than 4 neighbours per element (compiled limit)"; usim_destroy(h); return -1; }
-          e[cnt++] = ((int)nbrp[6 * i + k] << 16) | nbr[6 * i + k];
+          const int pr = nbrp[6 * i + k];
+          e[cnt++] = (pr << 16) | (pairs[2 * pr + 1] == i ? 0x8000 : 0) | nbr[6 * i + k]; // bit 15: this slider is the pair's SECOND element
         }
       for (; cnt < 4; cnt++) e[cnt] = (d.npair << 16) | i;
       n4[i] = make_int4(e[0], e[1], e[2], e[3]);
