@@ -27,6 +27,9 @@
 #define WPE 2
 #endif
 #define NT (32 * WPE)
+#ifndef MINB
+#define MINB (WPE <= 2 ? 8 : 16 / WPE) // resident CTAs per SM the register allocation is sized for
+#endif
 #define NPAIR_MAX 544
 
 struct __align__(16) WS {
@@ -59,7 +62,7 @@ struct __align__(16) WS {
   int ncon, okf;
   int cnt[2][WPE];                                     // cross-warp prefix of the contact compaction (double buffered)
 };
-static_assert(sizeof(WS) + 1024 <= 233472 / 8, "WS must leave room for 8 CTAs per SM");
+static_assert(sizeof(WS) + 1024 <= 233472 / MINB, "WS must leave room for MINB CTAs per SM");
 static_assert(2 * QPAD >= NPAIR_MAX + 1, "pg|s double as the pair scratch of K3");
 
 __device__ __forceinline__ void env_sync() {
@@ -248,7 +251,7 @@ __device__ __forceinline__ void chol7_solve(const float* L, float* x) {
 }
 
 // mode: 0 = env step, 1 = reset forward (no integration; initialises the running statistics)
-__global__ void __launch_bounds__(NT, 8) solve_kernel(
+__global__ void __launch_bounds__(NT, MINB) solve_kernel(
     int n, int mode, const uint8_t* __restrict__ mask, float* __restrict__ qpos, float* __restrict__ qvel, float* __restrict__ warm,
     float* __restrict__ task, const float* __restrict__ armbuf, PartTables pt, const int2* __restrict__ eq_pairs,
     float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
