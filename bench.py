@@ -208,7 +208,7 @@ def run_cuda(args):
     mean_ncon, mean_iters = float(diag[:, 22].mean()), float(diag[:, 20].mean())
 
     # ---------------- end to end through the host-buffer C-ABI call (H2D actions, D2H obs/reward/done inside)
-    acts_h = [a.cpu().numpy() for a in acts]
+    acts_h = [a.cpu().pin_memory().numpy() for a in acts]  # pinned host inputs, pinned host results (env.step_host)
     for i in range(min(args.warmup, 3)):
         env.step_host(acts_h[i % nact])
     barrier()

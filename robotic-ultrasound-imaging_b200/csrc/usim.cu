@@ -323,23 +323,37 @@ int usim_step(usim_handle* h, const float* act_dev, float* obs_dev, float* rew_d
   return 0;
 }
 
+// page-locked host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) can be the DMA end point itself
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int usim_step_host(usim_handle* h, const float* act, float* obs, float* rew, uint8_t* done, float* tobs, int auto_reset) {
   if (!h) return fail("usim_step_host: null handle");
+  if (!act) return fail("usim_step_host: act is required");
   if (activate(h)) return -1;
   cudaStream_t s = h->own_stream;
   size_t N = (size_t)h->n;
-  memcpy(h->h_act, act, N * h->adim * sizeof(float));
-  CK(cudaMemcpyAsync(h->d_act, h->h_act, N * h->adim * sizeof(float), cudaMemcpyHostToDevice, s));
+  // Caller buffers that are page-locked are used directly; pageable ones go through the library's pinned staging buffers.
+  const float* a_src = act;
+  if (!is_pinned(act)) { memcpy(h->h_act, act, N * h->adim * sizeof(float)); a_src = h->h_act; }
+  float* o_dst = obs && is_pinned(obs) ? obs : h->h_obs;
+  float* r_dst = rew && is_pinned(rew) ? rew : h->h_rew;
+  uint8_t* d_dst = done && is_pinned(done) ? done : h->h_done;
+  float* t_dst = tobs && is_pinned(tobs) ? tobs : h->h_tobs;
+  CK(cudaMemcpyAsync(h->d_act, a_src, N * h->adim * sizeof(float), cudaMemcpyHostToDevice, s));
   if (usim_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, tobs ? h->d_tobs : nullptr, auto_reset, s)) return -1;
-  CK(cudaMemcpyAsync(h->h_obs, h->d_obs, N * USIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h->h_rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h->h_done, h->d_done, N, cudaMemcpyDeviceToHost, s));
-  if (tobs) CK(cudaMemcpyAsync(h->h_tobs, h->d_tobs, N * USIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(o_dst, h->d_obs, N * USIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(r_dst, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(d_dst, h->d_done, N, cudaMemcpyDeviceToHost, s));
+  if (tobs) CK(cudaMemcpyAsync(t_dst, h->d_tobs, N * USIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  if (obs) memcpy(obs, h->h_obs, N * USIM_OBS_DIM * sizeof(float));
-  if (rew) memcpy(rew, h->h_rew, N * sizeof(float));
-  if (done) memcpy(done, h->h_done, N);
-  if (tobs) memcpy(tobs, h->h_tobs, N * USIM_OBS_DIM * sizeof(float));
+  if (obs && o_dst != obs) memcpy(obs, h->h_obs, N * USIM_OBS_DIM * sizeof(float));
+  if (rew && r_dst != rew) memcpy(rew, h->h_rew, N * sizeof(float));
+  if (done && d_dst != done) memcpy(done, h->h_done, N);
+  if (tobs && t_dst != tobs) memcpy(tobs, h->h_tobs, N * USIM_OBS_DIM * sizeof(float));
   return 0;
 }
 

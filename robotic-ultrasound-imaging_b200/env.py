@@ -152,9 +152,11 @@ class BatchedUltrasound:
         a = np.ascontiguousarray(actions, dtype=np.float32)
         assert a.shape == (self.num_envs, self.action_dim), a.shape
         if not hasattr(self, "_h_obs"):
+            # page-locked result buffers: the library DMAs straight into them (pageable caller buffers are staged inside the library)
             N = self.num_envs
-            self._h_obs, self._h_tobs = np.zeros((N, OBS_DIM), np.float32), np.zeros((N, OBS_DIM), np.float32)
-            self._h_rew, self._h_done = np.zeros(N, np.float32), np.zeros(N, np.uint8)
+            pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, pin_memory=True).numpy()
+            self._h_obs, self._h_tobs = pin(N, OBS_DIM), pin(N, OBS_DIM)
+            self._h_rew, self._h_done = pin(N), pin(N, dtype=torch.uint8)
         p = lambda x: C.c_void_p(x.ctypes.data)
         _lib.check(_lib.lib().usim_step_host(self._h, p(a), p(self._h_obs), p(self._h_rew), p(self._h_done), p(self._h_tobs), int(auto_reset)))
         return self._h_obs, self._h_rew, self._h_done, self._h_tobs

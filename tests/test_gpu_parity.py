@@ -421,3 +421,42 @@ def test_divergence_guard_ends_the_episode_with_finite_outputs():
     o, r, d, _ = env.step(torch.full((16, 6), 0.5), auto_reset=True)
     assert not bool(d.any()) and env.divergence_count == 2 and torch.isfinite(o).all()
     env.close()
+
+
+def test_host_buffer_call_matches_device_call():
+    """usim_step_host (the end-to-end entry point: host buffers, copies inside) returns exactly what usim_step leaves on the
+    device, for pageable caller buffers (staged through the library's pinned memory) and for page-locked ones (direct DMA)."""
+    import ctypes as C
+
+    from rui_b200 import _lib
+    opts = dict(seed=11, horizon=4, torso_solref_randomization=True, initial_probe_pos_randomization=True)
+    dev_env, host_env, pin_env = (_make(32, True, CC_TRACK, **opts) for _ in range(3))
+    for e in (dev_env, host_env, pin_env):
+        e.reset()
+    rng = np.random.default_rng(5)
+    N = 32
+    pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, pin_memory=True).numpy()
+    p_act, p_obs, p_rew, p_done, p_tobs = pin(N, 6), pin(N, 19), pin(N), pin(N, dtype=torch.uint8), pin(N, 19)
+    ptr = lambda x: C.c_void_p(x.ctypes.data)
+    for s in range(6):  # crosses the horizon: auto-reset and terminal observations are exercised
+        a = rng.uniform(0, 1, size=(N, 6)).astype(np.float32)
+        o, r, d, _ = dev_env.step(torch.as_tensor(a), auto_reset=True)
+        tob = dev_env.term_obs.cpu().numpy()
+        # pageable numpy buffers of the caller
+        ho, hr, hd, ht = (np.zeros((N, 19), np.float32), np.zeros(N, np.float32), np.zeros(N, np.uint8), np.zeros((N, 19), np.float32))
+        _lib.check(_lib.lib().usim_step_host(host_env._h, ptr(a), ptr(ho), ptr(hr), ptr(hd), ptr(ht), 1))
+        # page-locked buffers
+        p_act[:] = a
+        _lib.check(_lib.lib().usim_step_host(pin_env._h, ptr(p_act), ptr(p_obs), ptr(p_rew), ptr(p_done), ptr(p_tobs), 1))
+        for go, gr, gd, gt in ((ho, hr, hd, ht), (p_obs, p_rew, p_done, p_tobs)):
+            assert np.array_equal(go, o.cpu().numpy()) and np.array_equal(gr, r.cpu().numpy()) and np.array_equal(gd, d.cpu().numpy()), s
+            if gd.any():
+                assert np.array_equal(gt[gd.astype(bool)], tob[gd.astype(bool)]), s
+        assert bool(d.all()) == (s == 3)
+    # the Python wrapper (pinned result buffers) gives the same numbers
+    a = rng.uniform(0, 1, size=(N, 6)).astype(np.float32)
+    o, r, d, _ = dev_env.step(torch.as_tensor(a), auto_reset=True)
+    ho, hr, hd, _ = host_env.step_host(a)
+    assert np.array_equal(ho, o.cpu().numpy()) and np.array_equal(hr, r.cpu().numpy()) and np.array_equal(hd, d.cpu().numpy())
+    for e in (dev_env, host_env, pin_env):
+        e.close()
