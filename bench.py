@@ -251,6 +251,9 @@ def run_cuda(args):
         }
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
+            if args.cpu_steps <= 0:  # bounded sample: ~15 s of CPU work, sized from a short calibration run
+                r0, _, _, _ = cpu_baseline(threads, 4)
+                args.cpu_steps = int(min(max(15.0 * r0 / threads, 20), 5000))
             rate, dt, _, _ = cpu_baseline(threads, args.cpu_steps)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
                                     "sample": f"{threads} envs x {args.cpu_steps} steps of the same workload, float64 oracle with the "
@@ -271,7 +274,7 @@ def main():
     ap.add_argument("--rebuilds", type=int, default=0, help="preconditioner rebuilds allowed per solve (0: library default)")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--cpu-steps", type=int, default=0, help="env steps per host thread of the cpu_baseline sample (0: ~15 s of CPU work)")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch of the dominant kernel from an ncu capture")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -31,6 +31,15 @@
 #define MINB (WPE <= 2 ? 8 : 16 / WPE) // resident CTAs per SM the register allocation is sized for
 #endif
 #define NPAIR_MAX 544
+// unroll factor of the NT-strided loops inside the CG iteration (each warp runs only 4-5 trips of a slider loop, 1-2 of a contact loop):
+// trades ILP against the size of the loop body in the instruction cache (`no_instruction` is the top stall with 16 warps per SM)
+#define USIM_STR2(x) #x
+#define USIM_STR(x) USIM_STR2(x)
+// measured, 4096 envs: compiler default 6.52 M steps/s (7456 SASS instructions), unroll 1: 6.61 M (7096), unroll 2: 5.79 M (8296)
+#ifndef HOT_UNROLL
+#define HOT_UNROLL 1
+#endif
+#define PRAGMA_HOT _Pragma(USIM_STR(unroll HOT_UNROLL))
 
 struct __align__(16) WS {
   // ---- landing zones of the 1-D TMA bulk copies (whole HBM rows, 16-byte aligned; written back the same way) ----
@@ -562,6 +571,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     if (dm.soft) {
       const v3 ivl = mtv(R, ld3(in + 7)); // R^T in_v
       const float Dt = w.Dt, dts = Dt * S4[0];
+      PRAGMA_HOT
       for (int i = tid; i < np; i += NT) {
         float xi = in[13 + i];
         v3 ah = xyz(pt.ax4[i]);
@@ -611,6 +621,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
   // before projection on the contact frame (needs dv of `in`, written by applyH)
   auto contactJ = [&](const float* in, float (*out)[DEV_MAXC], bool sub_aref) {
     v3 V = ld3(w.dv), W = ld3(w.dv + 3), iv = ld3(w.dv + 6), iw = ld3(w.dv + 9);
+    PRAGMA_HOT
     for (int c = tid; c < ncon; c += NT) {
       int type = w.ctype[c], i = w.cpart[c];
       v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]);
@@ -638,6 +649,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
 #pragma unroll
     for (int k = 0; k < 15; k++) g[k] = 0.f;
     g[13] = hx2; g[14] = rhs2;
+    PRAGMA_HOT
     for (int c = tid; c < ncon; c += NT) {
       int type = w.ctype[c], i = w.cpart[c], zone;
       float fr, mu, Dn = w.cD[c];
@@ -662,6 +674,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     tsum_to(g, lane, w.rg[wrp]);
     env_sync();
     // slider rows: the owner contact of each slider adds the shares of its (at most 3) contacts in slot order -- no atomics
+    PRAGMA_HOT
     for (int c = tid; c < ncon; c += NT) {
       const int i = w.cpart[c];
       if (i >= 0 && w.cslot[i] == c) w.grad[13 + i] += slider_gather(w.cfs, c, i);
@@ -692,6 +705,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     float a[10];
 #pragma unroll
     for (int k = 0; k < 10; k++) a[k] = 0.f;
+    PRAGMA_HOT
     for (int i = tid; i < np; i += NT) {
       float g = w.grad[13 + i], gi = g * w.dg[i];
       v3 ah = xyz(pt.ax4[i]);
@@ -737,6 +751,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
         for (int k = 7; k < 13; k++) b[1] += gd[k] * gd[k];
       }
     }
+    PRAGMA_HOT
     for (int i = tid; i < np; i += NT) {
       float g = w.grad[13 + i];
       v3 ah = xyz(pt.ax4[i]);
@@ -761,14 +776,19 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
   auto build_precond = [&]() {
 #pragma unroll 1
     for (int i = tid; i < np; i += NT) w.dg[i] = w.dgm[i] + w.Dt;
-    float acc[42]; // packed upper triangles of the 6x6 wrench-space Hessians: [0..20] torso side (about P), [21..41] probe side (about the site)
+    // Packed upper triangles of the 6x6 wrench-space Hessians: side 0 = torso (about P), side 1 = probe (about the site).  The two
+    // sides are two trips of ONE rolled loop (one copy of the body in the instruction cache; only the few probe-particle contacts
+    // are visited by both trips).  Entry l of a triangle lands in lane l of every warp, then in row `wrp` of rb1 / rb2.
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+    float acc[21];
 #pragma unroll
-    for (int k = 0; k < 42; k++) acc[k] = 0.f;
+    for (int k = 0; k < 21; k++) acc[k] = 0.f;
 #pragma unroll 1
     for (int c = tid; c < ncon; c += NT) {
       int zone = w.czone[c], type = w.ctype[c], i = w.cpart[c];
-      w.sc[0][c] = 0.f; w.sc[1][c] = 0.f; w.sc[2][c] = 0.f; w.cfs[c] = 0.f; // this contact's share of its slider's (K a, a^T K a)
-      if (zone == 0) continue;
+      if (side == 0) { w.sc[0][c] = 0.f; w.sc[1][c] = 0.f; w.sc[2][c] = 0.f; w.cfs[c] = 0.f; } // this contact's share of its slider's (K a, a^T K a)
+      if (zone == 0 || type == (side == 0 ? 2 : 0)) continue;
       const float Dn = w.cD[c], Dtn = Dn * dm.impratio;
       const v3 pos = mk(w.cpos[0][c], w.cpos[1][c], w.cpos[2][c]), nn = mk(w.cn[0][c], w.cn[1][c], w.cn[2][c]);
       // World Hessian of the cone cost wrt the contact-point acceleration, K = c_i I + c_n n n^T + c_u u u^T + c_g g g^T
@@ -797,7 +817,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
       Ks[4] = cnn * nn.y * nn.z + cu * u.y * u.z + cg * gv.y * gv.z;
       Ks[5] = ci + cnn * nn.z * nn.z + cu * u.z * u.z + cg * gv.z * gv.z;
       const v3 K0 = mk(Ks[0], Ks[1], Ks[2]), K1 = mk(Ks[1], Ks[3], Ks[4]), K2 = mk(Ks[2], Ks[4], Ks[5]);
-      if (type != 2) { // slider of this particle: K a_i and a_i^T K a_i, gathered per slider by its owner slot below
+      if (side == 0) { // slider of this particle: K a_i and a_i^T K a_i, gathered per slider by its owner slot below
         v3 aw = mv(R, xyz(pt.ax4[i]));
         v3 ka = mk(dot(K0, aw), dot(K1, aw), dot(K2, aw));
         w.sc[0][c] = ka.x; w.sc[1][c] = ka.y; w.sc[2][c] = ka.z;
@@ -805,24 +825,18 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
       }
       // wrench-space Hessian [I; [r]x] K [I, [r]x^T] (force; torque about the reference point), packed upper triangle:
       // upper-right block rows r x K_i, lower-right block columns r x (column of the upper-right block)
-      auto accum = [&](float* A21, v3 r) {
+      {
+        const v3 r = pos - (side == 0 ? P : site);
         const v3 B0 = cross(r, K0), B1 = cross(r, K1), B2 = cross(r, K2); // rows of K [r]x^T
         const v3 C0 = cross(r, mk(B0.x, B1.x, B2.x)), C1 = cross(r, mk(B0.y, B1.y, B2.y)), C2 = cross(r, mk(B0.z, B1.z, B2.z)); // columns of [r]x K [r]x^T
-        A21[tri6(0, 0)] += Ks[0]; A21[tri6(0, 1)] += Ks[1]; A21[tri6(0, 2)] += Ks[2]; A21[tri6(1, 1)] += Ks[3]; A21[tri6(1, 2)] += Ks[4]; A21[tri6(2, 2)] += Ks[5];
-        A21[tri6(0, 3)] += B0.x; A21[tri6(0, 4)] += B0.y; A21[tri6(0, 5)] += B0.z;
-        A21[tri6(1, 3)] += B1.x; A21[tri6(1, 4)] += B1.y; A21[tri6(1, 5)] += B1.z;
-        A21[tri6(2, 3)] += B2.x; A21[tri6(2, 4)] += B2.y; A21[tri6(2, 5)] += B2.z;
-        A21[tri6(3, 3)] += C0.x; A21[tri6(3, 4)] += C1.x; A21[tri6(3, 5)] += C2.x; A21[tri6(4, 4)] += C1.y; A21[tri6(4, 5)] += C2.y; A21[tri6(5, 5)] += C2.z;
-      };
-      if (type != 2) accum(acc, pos - P);
-      if (type != 0) accum(acc + 21, pos - site);
+        acc[tri6(0, 0)] += Ks[0]; acc[tri6(0, 1)] += Ks[1]; acc[tri6(0, 2)] += Ks[2]; acc[tri6(1, 1)] += Ks[3]; acc[tri6(1, 2)] += Ks[4]; acc[tri6(2, 2)] += Ks[5];
+        acc[tri6(0, 3)] += B0.x; acc[tri6(0, 4)] += B0.y; acc[tri6(0, 5)] += B0.z;
+        acc[tri6(1, 3)] += B1.x; acc[tri6(1, 4)] += B1.y; acc[tri6(1, 5)] += B1.z;
+        acc[tri6(2, 3)] += B2.x; acc[tri6(2, 4)] += B2.y; acc[tri6(2, 5)] += B2.z;
+        acc[tri6(3, 3)] += C0.x; acc[tri6(3, 4)] += C1.x; acc[tri6(3, 5)] += C2.x; acc[tri6(4, 4)] += C1.y; acc[tri6(4, 5)] += C2.y; acc[tri6(5, 5)] += C2.z;
+      }
     }
-    // entry l of each packed triangle lands in lane l of every warp, then in row `wrp` of rb1 / rb2
-    {
-      float(&lo21)[21] = *reinterpret_cast<float(*)[21]>(acc);
-      float(&hi21)[21] = *reinterpret_cast<float(*)[21]>(acc + 21);
-      tsum_to(lo21, lane, w.rb1[wrp]);
-      tsum_to(hi21, lane, w.rb2[wrp]);
+    tsum_to(acc, lane, side == 0 ? w.rb1[wrp] : w.rb2[wrp]);
     }
     env_sync();
     const float kf = lane < 21 ? rd(w.rb1, lane) : 0.f;
@@ -937,6 +951,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     float hx2 = 0.f, rhs2 = 0.f;
     if (init) {
       // grad holds rhs until here
+      PRAGMA_HOT
       for (int i = tid; i < nv; i += NT) {
         float r = w.grad[i], hx = w.Hx[i] - r;
         w.Hx[i] = hx; w.grad[i] = hx;
@@ -949,6 +964,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
 #pragma unroll 1
       for (int ls = 0; ls < 8; ls++) {
         float d1 = 0.f, d2 = 0.f;
+        PRAGMA_HOT
         for (int c = tid; c < ncon; c += NT) {
           float fr, mu, a1, a2, Dn = w.cD[c];
           contact_params(w.ctype[c], fr, mu);
@@ -980,11 +996,13 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
         if (an == alpha) break;
         alpha = an;
       }
+      PRAGMA_HOT
       for (int i = tid; i < nv; i += NT) {
         float hx = w.Hx[i] + alpha * w.hs[i];
         w.x[i] += alpha * w.s[i]; w.Hx[i] = hx; w.grad[i] = hx;
         hx2 += hx * hx;
       }
+      PRAGMA_HOT
       for (int c = tid; c < ncon; c += NT) {
         w.cjar[0][c] += alpha * w.cjv[0][c]; w.cjar[1][c] += alpha * w.cjv[1][c]; w.cjar[2][c] += alpha * w.cjv[2][c];
       }
@@ -1008,6 +1026,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     gpg = gpn;
 #pragma unroll
     for (int k = 0; k < 4; k++) S4[k] = -rd(w.rq, 2 + k) + beta * S4[k];
+    PRAGMA_HOT
     for (int i = tid; i < nv; i += NT) w.s[i] = -w.pg[i] + beta * w.s[i];
     env_sync();
   }
