@@ -83,17 +83,12 @@ __device__ __forceinline__ void osc_set_goal(const float* act, const ArmKin& k, 
 }
 
 // mode: 0 = env step (controller runs), 1 = reset forward (ctrl = 0)
-__global__ void __launch_bounds__(64) arm_kernel(int n, int mode, const uint8_t* __restrict__ mask, const float* __restrict__ qpos,
-                                                 const float* __restrict__ qvel, const float* __restrict__ act,
-                                                 float* __restrict__ task, float* __restrict__ armbuf) {
-  int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= n) return;
-  if (mask && !mask[env]) return;
+// mode 0: env step (OSC torques from the action); mode 1: forward pass after a reset (ctrl = 0)
+// (q, qd: the arm joint positions / velocities of this env, in registers: the caller may have just written them to HBM itself)
+__device__ __forceinline__ void arm_forward(int env, int mode, const float (&q)[7], const float (&qd)[7],
+                                            const float* __restrict__ act, float* __restrict__ task, float* __restrict__ armbuf) {
   float* ts = task + (size_t)env * USIM_TASK_DIM;
   if (mode == 0 && ts[USIM_TS_DONE] != 0.f) return; // terminated env: frozen until reset
-  float q[7], qd[7];
-#pragma unroll
-  for (int j = 0; j < 7; j++) { q[j] = qpos[(size_t)env * QPAD + j]; qd[j] = qvel[(size_t)env * QPAD + j]; }
   float* ab = armbuf + (size_t)env * ARMBUF;
 
   ArmKin k;
@@ -319,15 +314,33 @@ __global__ void __launch_bounds__(64) arm_kernel(int n, int mode, const uint8_t*
   ab[AB_QUAT] = qx[0]; ab[AB_QUAT + 1] = qx[1]; ab[AB_QUAT + 2] = qx[2]; ab[AB_QUAT + 3] = qx[3];
 }
 
+// One thread per env.  Also clears `done` (frozen envs report done = 0; the solve kernel sets it for the envs it steps).
+__global__ void __launch_bounds__(64) arm_kernel(int n, const float* __restrict__ qpos, const float* __restrict__ qvel,
+                                                 const float* __restrict__ act, float* __restrict__ task, float* __restrict__ armbuf,
+                                                 uint8_t* __restrict__ done) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  if (done) done[env] = 0;
+  float q[7], qd[7];
+#pragma unroll
+  for (int j = 0; j < 7; j++) { q[j] = qpos[(size_t)env * QPAD + j]; qd[j] = qvel[(size_t)env * QPAD + j]; }
+  arm_forward(env, 0, q, qd, act, task, armbuf);
+}
+
 // ---------------------------------------------------------------- reset (ultrasound.py:416-477, :749-887)
 // One thread per env: Philox draws keyed by (seed, global env id, episode), trajectory, DLS inverse
-// kinematics for the initial joint pose, state initialisation.  The forward pass that fills the
-// contact-force statistics and the observation is run afterwards (arm_kernel mode 1 + solve kernel).
+// kinematics for the initial joint pose, state initialisation, then the arm part of the post-reset forward pass
+// (sim.forward() with ctrl = 0, ultrasound.py:431); the solve kernel (mode 1) that fills the contact-force statistics and the
+// observation runs afterwards.  With `tobs` the observation of the terminal step is kept first (SB3 `terminal_observation`).
 __global__ void __launch_bounds__(64) reset_kernel(int n, const uint8_t* __restrict__ mask, float* __restrict__ qpos, float* __restrict__ qvel,
-                                                   float* __restrict__ warm, float* __restrict__ task) {
+                                                   float* __restrict__ warm, float* __restrict__ task, float* __restrict__ armbuf,
+                                                   const float* __restrict__ obs, float* __restrict__ tobs) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= n) return;
   if (mask && !mask[env]) return;
+  if (obs && tobs) {
+    for (int i = 0; i < USIM_OBS_DIM; i++) tobs[(size_t)env * USIM_OBS_DIM + i] = obs[(size_t)env * USIM_OBS_DIM + i];
+  }
   float* ts = task + (size_t)env * USIM_TASK_DIM;
   unsigned ep = (unsigned)ts[USIM_TS_EPISODE], gid = (unsigned)(dm.env_off + env), r[4];
   float kst = -dm.solref_smooth[0], bst = -dm.solref_smooth[1];
@@ -426,4 +439,6 @@ __global__ void __launch_bounds__(64) reset_kernel(int n, const uint8_t* __restr
   st3(ts + USIM_TS_GOAL_POS, k.site); // osc.reset_goal
 #pragma unroll
   for (int i = 0; i < 9; i++) ts[USIM_TS_GOAL_ORI + i] = k.Rs[i];
+  const float qd0[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  arm_forward(env, 1, q, qd0, nullptr, task, armbuf);
 }

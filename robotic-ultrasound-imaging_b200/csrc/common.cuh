@@ -103,7 +103,9 @@ __device__ __forceinline__ v3 symv(const float* I, v3 a) {
   return v3{I[0] * a.x + I[3] * a.y + I[4] * a.z, I[3] * a.x + I[1] * a.y + I[5] * a.z, I[4] * a.x + I[5] * a.y + I[2] * a.z};
 }
 
-// in-place Cholesky of a dense n x n (row-major, lower), n compile-time
+// in-place Cholesky of a dense n x n (row-major, lower), n compile-time.  Every loop has a CONSTANT trip count with a
+// predicate inside: triangular bounds made the compiler keep inner loops rolled and index the (register) matrix dynamically,
+// which put it in local memory.
 template <int N>
 __device__ __forceinline__ bool chol(float* A) {
   bool ok = true;
@@ -111,39 +113,21 @@ __device__ __forceinline__ bool chol(float* A) {
   for (int j = 0; j < N; j++) {
     float s = A[j * N + j];
 #pragma unroll
-    for (int k = 0; k < j; k++) s -= A[j * N + k] * A[j * N + k];
+    for (int k = 0; k < N; k++)
+      if (k < j) s -= A[j * N + k] * A[j * N + k];
     if (!(s > 0.f)) { ok = false; s = 1e-20f; }
     s = sqrtf(s);
     A[j * N + j] = s;
     float inv = 1.f / s;
 #pragma unroll
-    for (int i = j + 1; i < N; i++) {
-      float t = A[i * N + j];
+    for (int i = 0; i < N; i++) {
+      if (i > j) {
+        float t = A[i * N + j];
 #pragma unroll
-      for (int k = 0; k < j; k++) t -= A[i * N + k] * A[j * N + k];
-      A[i * N + j] = t * inv;
-    }
-  }
-  return ok;
-}
-// rolled variant for rarely executed code (small SASS): A in shared/global memory
-__device__ __noinline__ bool chol_rolled(float* A, int n) {
-  bool ok = true;
-#pragma unroll 1
-  for (int j = 0; j < n; j++) {
-    float s = A[j * n + j];
-#pragma unroll 1
-    for (int k = 0; k < j; k++) s -= A[j * n + k] * A[j * n + k];
-    if (!(s > 0.f)) { ok = false; s = 1e-20f; }
-    s = sqrtf(s);
-    A[j * n + j] = s;
-    float inv = 1.f / s;
-#pragma unroll 1
-    for (int i = j + 1; i < n; i++) {
-      float t = A[i * n + j];
-#pragma unroll 1
-      for (int k = 0; k < j; k++) t -= A[i * n + k] * A[j * n + k];
-      A[i * n + j] = t * inv;
+        for (int k = 0; k < N; k++)
+          if (k < j) t -= A[i * N + k] * A[j * N + k];
+        A[i * N + j] = t * inv;
+      }
     }
   }
   return ok;
@@ -154,14 +138,16 @@ __device__ __forceinline__ void chol_solve(const float* L, float* x) {
   for (int i = 0; i < N; i++) {
     float t = x[i];
 #pragma unroll
-    for (int k = 0; k < i; k++) t -= L[i * N + k] * x[k];
+    for (int k = 0; k < N; k++)
+      if (k < i) t -= L[i * N + k] * x[k];
     x[i] = t / L[i * N + i];
   }
 #pragma unroll
   for (int i = N - 1; i >= 0; i--) {
     float t = x[i];
 #pragma unroll
-    for (int k = i + 1; k < N; k++) t -= L[k * N + i] * x[k];
+    for (int k = 0; k < N; k++)
+      if (k > i) t -= L[k * N + i] * x[k];
     x[i] = t / L[i * N + i];
   }
 }

@@ -263,10 +263,15 @@ static int activate(usim_handle* h) {
   return 0;
 }
 
+// forward pass: mode 0 = env step (arm kernel + solve kernel), mode 1 = post-reset forward (solve kernel only: the reset kernel
+// has already run the arm part)
 static int launch_forward(usim_handle* h, int mode, const uint8_t* mask, const float* act, float* obs, float* rew, uint8_t* done,
                           cudaStream_t s, bool timed) {
   int n = h->n;
-  arm_kernel<<<(n + 63) / 64, 64, 0, s>>>(n, mode, mask, h->qpos, h->qvel, act, h->task, h->armbuf);
+  if (mode == 0) {
+    arm_kernel<<<(n + 63) / 64, 64, 0, s>>>(n, h->qpos, h->qvel, act, h->task, h->armbuf, done);
+    h->launches += 1;
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timed && h->pending.size() >= 4096) timed = false; // bounded: caller drains with usim_kernel_time
   if (timed) {
@@ -280,7 +285,7 @@ static int launch_forward(usim_handle* h, int mode, const uint8_t* mask, const f
     CK(cudaEventRecord(e1, s));
     h->pending.emplace_back(e0, e1);
   }
-  h->launches += 2;
+  h->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }
@@ -289,33 +294,23 @@ int usim_reset(usim_handle* h, const uint8_t* mask_dev, float* obs_dev, void* st
   if (!h) return fail("usim_reset: null handle");
   if (activate(h)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
-  reset_kernel<<<(h->n + 63) / 64, 64, 0, s>>>(h->n, mask_dev, h->qpos, h->qvel, h->warm, h->task);
+  reset_kernel<<<(h->n + 63) / 64, 64, 0, s>>>(h->n, mask_dev, h->qpos, h->qvel, h->warm, h->task, h->armbuf, nullptr, nullptr);
   h->launches += 1;
   CK(cudaGetLastError());
   return launch_forward(h, 1, mask_dev, nullptr, obs_dev, nullptr, nullptr, s, false);
 }
 
-__global__ void copy_terminal_obs(int n, const uint8_t* __restrict__ done, const float* __restrict__ obs, float* __restrict__ tobs) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * USIM_OBS_DIM) return;
-  if (done[i / USIM_OBS_DIM]) tobs[i] = obs[i];
-}
-
+// One env step = 4 launches: arm_kernel (also clears `done`), solve_kernel, and for auto-reset reset_kernel (terminal observation,
+// reset, arm forward; masked by `done`) + solve_kernel in forward-only mode (masked by `done`).
 int usim_step(usim_handle* h, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, float* term_obs_dev,
               int auto_reset, void* stream) {
   if (!h) return fail("usim_step: null handle");
   if (!act_dev || !done_dev) return fail("usim_step: act_dev and done_dev are required");
   if (activate(h)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
-  CK(cudaMemsetAsync(done_dev, 0, h->n, s)); // frozen (already done) envs report done = 0 and are skipped
   if (launch_forward(h, 0, nullptr, act_dev, obs_dev, rew_dev, done_dev, s, true)) return -1;
   if (auto_reset) {
-    if (term_obs_dev && obs_dev) {
-      int tot = h->n * USIM_OBS_DIM;
-      copy_terminal_obs<<<(tot + 255) / 256, 256, 0, s>>>(h->n, done_dev, obs_dev, term_obs_dev);
-      h->launches += 1;
-    }
-    reset_kernel<<<(h->n + 63) / 64, 64, 0, s>>>(h->n, done_dev, h->qpos, h->qvel, h->warm, h->task);
+    reset_kernel<<<(h->n + 63) / 64, 64, 0, s>>>(h->n, done_dev, h->qpos, h->qvel, h->warm, h->task, h->armbuf, obs_dev, term_obs_dev);
     h->launches += 1;
     if (launch_forward(h, 1, done_dev, nullptr, obs_dev, nullptr, nullptr, s, false)) return -1;
   }
