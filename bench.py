@@ -251,9 +251,9 @@ def run_cuda(args):
         }
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            if args.cpu_steps <= 0:  # bounded sample: ~15 s of CPU work, sized from a short calibration run
+            if args.cpu_steps <= 0:  # bounded sample: 10-20 s of CPU work, sized from a short calibration run
                 r0, _, _, _ = cpu_baseline(threads, 4)
-                args.cpu_steps = int(min(max(15.0 * r0 / threads, 20), 5000))
+                args.cpu_steps = int(min(max(22.0 * r0 / threads, 20), 5000))
             rate, dt, _, _ = cpu_baseline(threads, args.cpu_steps)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
                                     "sample": f"{threads} envs x {args.cpu_steps} steps of the same workload, float64 oracle with the "
