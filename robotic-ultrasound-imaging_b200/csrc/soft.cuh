@@ -212,13 +212,13 @@ __device__ __forceinline__ void seg_seg(v3 p1, v3 q1, v3 p2, v3 q2, v3& c1, v3& 
 }
 
 // In-place Cholesky of TWO 7x7 matrices (row-major, pitch 7, both triangles valid on entry) held in shared memory, by one warp:
-// one matrix row per lane (lanes 0-6 -> A0, lanes 8-14 -> A1), right-looking, rows in registers, columns exchanged by shuffles.
+// one matrix row per lane (lanes 0-6 -> A0, lanes 8-14 -> A1; A1 may be null), right-looking, rows in registers, columns exchanged by shuffles.
 // The factors are left in the lower triangles with their diagonals INVERTED (the solves multiply).  Returns false in the lanes of a
 // matrix that met a non-positive pivot (the pivot is clamped).  Every loop has a constant trip count: nothing is indexed dynamically.
 __device__ __forceinline__ bool chol7_warp2(float* A0, float* A1, int lane) {
   const int base = lane & 8, r = lane & 7;
-  const bool act = lane < 16 && r < 7;
   float* A = base ? A1 : A0;
+  const bool act = lane < 16 && r < 7 && A != nullptr; // A1 == nullptr: factorise A0 only
   float row[7];
 #pragma unroll
   for (int k = 0; k < 7; k++) row[k] = act ? A[r * 7 + k] : (k == r ? 1.f : 0.f);
@@ -1063,7 +1063,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
       w.dv[lane] = s;
     }
     env_sync();
-    if (wrp == 0) chol7_warp2(w.Pa, w.Pa, lane);
+    if (wrp == 0) chol7_warp2(w.Pa, nullptr, lane);
     env_sync();
     {
       float b[7];
