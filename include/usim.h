@@ -157,8 +157,11 @@ int usim_step(usim_handle* h, const float* act_dev, float* obs_dev, float* rew_d
               uint8_t* done_dev, float* term_obs_dev, int auto_reset, void* stream);
 
 /* Convenience for host callers (the end-to-end path of bench.py and of the
- * single-env robosuite-style API): HOST buffers, pinned staging and the
- * H2D/D2H copies are done inside the call; synchronises the stream. */
+ * single-env robosuite-style API): HOST buffers; the H2D/D2H copies are done
+ * inside the call, which synchronises the library's stream.  A buffer that is
+ * page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) is the DMA
+ * end point itself; a pageable one is staged through the library's pinned
+ * memory (one extra host memcpy). */
 int usim_step_host(usim_handle* h, const float* act_host, float* obs_host, float* rew_host,
                    uint8_t* done_host, float* term_obs_host, int auto_reset);
 
