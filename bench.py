@@ -168,7 +168,7 @@ def run_cuda(args):
         per_gpu = args.envs
     else:
         per_gpu = 4096 if world == 1 else 65536 // world
-    env = BatchedUltrasound(per_gpu, device=dev, seed=SEED, env_id_offset=rank * per_gpu, solver_iterations=args.iters, precond_rebuilds=args.rebuilds, **ENV_OPTS)
+    env = BatchedUltrasound(per_gpu, device=dev, seed=SEED, env_id_offset=rank * per_gpu, solver_iterations=args.iters, precond_rebuilds=args.rebuilds, **({"solver_tolerance": args.tol} if args.tol else {}), **ENV_OPTS)
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(SEED + rank)
@@ -237,7 +237,7 @@ def run_cuda(args):
                                     f"BASELINE config 4: soft-torso sweep task, {total_envs} envs over {world} GPU(s)"),
                        "envs_total": total_envs, "envs_per_gpu": per_gpu, "controller": "OSC_POSE tracking (rl_config.yaml)",
                        "actions": "U[0,1]^6 (torch.Generator seed 3)", "auto_reset": True, "early_termination": False,
-                       "solver": f"PCG cap {args.iters}", "mean_ncon": mean_ncon, "mean_solver_iters": mean_iters,
+                       "solver": f"PCG cap {args.iters}, relative gradient tolerance {args.tol or 1e-5:g}", "mean_ncon": mean_ncon, "mean_solver_iters": mean_iters,
                        "l2": "state (~27 MB at 4096 envs) is smaller than L2; 256 MiB memset between steps, outside the per-step events"
                              if flush is not None else "not flushed"},
             "clocks": clocks,
@@ -272,6 +272,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: BASELINE configs)")
     ap.add_argument("--iters", type=int, default=40, help="solver iteration cap")
     ap.add_argument("--rebuilds", type=int, default=0, help="preconditioner rebuilds allowed per solve (0: library default)")
+    ap.add_argument("--tol", type=float, default=0.0, help="device solver tolerance (0: library default 1e-5)")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=0, help="env steps per host thread of the cpu_baseline sample (0: ~15 s of CPU work)")

@@ -140,7 +140,7 @@ def make_config(
     seed: int = 0,
     env_id_offset: int = 0,
     solver_iterations: int = 40,
-    solver_tolerance: float = 3e-6,
+    solver_tolerance: float = 1e-5,
     precond_rebuilds: int = 0,
     reset_eef_bias=ART_RESET_EEF_BIAS,
 ) -> UsimConfig:

@@ -83,7 +83,7 @@ class BatchedUltrasound:
         seed: int = 0,
         env_id_offset: int = 0,
         solver_iterations: int = 40,
-        solver_tolerance: float = 3e-6,
+        solver_tolerance: float = 1e-5,
         scene_params: Optional[SceneParams] = None,
         **cfg_kwargs,
     ):

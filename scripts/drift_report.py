@@ -24,8 +24,9 @@ CC_FIXED = dict(type="OSC_POSE", input_max=1, input_min=-1, output_max=[0.05] * 
 CC_TRACK = dict(CC_FIXED, impedance_mode="tracking")
 
 
-def run(soft, cc, steps, n, act_fn, **kw):
-    env = BatchedUltrasound(n, soft_torso=soft, controller_configs=cc, control_freq=500, horizon=steps + 1, seed=3, **kw)
+def run(soft, cc, steps, n, act_fn, tol=None, **kw):
+    ekw = dict(kw, solver_tolerance=tol) if tol else kw  # device-side solver tolerance (the oracle always solves to 1e-10)
+    env = BatchedUltrasound(n, soft_torso=soft, controller_configs=cc, control_freq=500, horizon=steps + 1, seed=3, **ekw)
     env.reset()
     q, v, w, t = [x.cpu().numpy().astype(np.float64) for x in env.get_state()]
     orcs = []
@@ -78,8 +79,9 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default="")
     ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--tol", type=float, default=0.0, help="device solver tolerance (default: the library default)")
     a = ap.parse_args()
-    out = {"rigid_press_config2": run(False, CC_FIXED, a.steps, 2, press_then_random),
-           "soft_sweep_config3": run(True, CC_TRACK, a.steps, 3, rnd, torso_solref_randomization=True, initial_probe_pos_randomization=True)}
+    out = {"rigid_press_config2": run(False, CC_FIXED, a.steps, 2, press_then_random, tol=a.tol or None),
+           "soft_sweep_config3": run(True, CC_TRACK, a.steps, 3, rnd, tol=a.tol or None, torso_solref_randomization=True, initial_probe_pos_randomization=True)}
     if a.json:
         json.dump(out, open(a.json, "w"), indent=1)
