@@ -31,6 +31,20 @@
 #define MINB (WPE <= 2 ? 8 : 16 / WPE) // resident CTAs per SM the register allocation is sized for
 #endif
 #define NPAIR_MAX 544
+// Slider block of the preconditioner, D - W (D: diagonal, W: the pair couplings of the shell grid), inverted by a polynomial in
+// N = D^-1 W.  PREC3 = 0: second order, D^-1 (I + N).  PREC3 = 1: third order with Chebyshev weights, D^-1 (I + c (N + N^2)),
+// c = 4 / (4 - 3 rho^2): the cubic (1 - x) p(x) = 1 - T3(x / rho) / T3(1 / rho) deviates least from 1 on the spectrum [-rho, rho]
+// of N.  rho ~ 0.7 for this model (sum of a slider's pair D over its diagonal) -> c = 1.6; measured at 4096 envs:
+// second order 0.513 ms, c = 1.0 (plain Neumann) 0.513, 1.4: 0.485, 1.7: 0.483, 2.0: 0.488, 2.4: 0.506, 3.0: 0.578.
+#ifndef PREC3
+#define PREC3 1
+#endif
+#ifndef CHEB_C
+#define CHEB_C 1.6f
+#endif
+#ifndef LS_MAX
+#define LS_MAX 8 // evaluations of phi'(alpha) per line search (Newton with bracketing; 1 = one quadratic step, unverified)
+#endif
 // unroll factor of the NT-strided loops inside the CG iteration (each warp runs only 4-5 trips of a slider loop, 1-2 of a contact loop):
 // trades ILP against the size of the loop body in the instruction cache (`no_instruction` is the top stall with 16 warps per SM)
 #define USIM_STR2(x) #x
@@ -751,6 +765,16 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
         for (int k = 7; k < 13; k++) b[1] += gd[k] * gd[k];
       }
     }
+#if PREC3
+    PRAGMA_HOT
+    for (int i = tid; i < np; i += NT) {
+      const int4 e = pt.nb4[i];
+      float nb = w.Dp[e.x >> 16] * w.hs[13 + (e.x & 0x7fff)] + w.Dp[e.y >> 16] * w.hs[13 + (e.y & 0x7fff)] +
+                 w.Dp[e.z >> 16] * w.hs[13 + (e.z & 0x7fff)] + w.Dp[e.w >> 16] * w.hs[13 + (e.w & 0x7fff)];
+      w.pg[13 + i] = nb * w.dg[i];
+    }
+    env_sync();
+#endif
     PRAGMA_HOT
     for (int i = tid; i < np; i += NT) {
       float g = w.grad[13 + i];
@@ -761,10 +785,18 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
         by += w.sk[0][cs] * y[0] + w.sk[1][cs] * y[1] + w.sk[2][cs] * y[2] + w.sc[0][cs] * y[3] + w.sc[1][cs] * y[4] + w.sc[2][cs] * y[5];
       // slider block D - W (W: the pair couplings) inverted to second order, D^-1 + D^-1 W D^-1: hs holds D^-1 grad
       const int4 e = pt.nb4[i];
+#if PREC3
+      // third order with Chebyshev weights: z0 + c (z1 + z2), z1 = D^-1 W z0 (in pg), z2 = D^-1 W z1
+      float nb = w.Dp[e.x >> 16] * w.pg[13 + (e.x & 0x7fff)] + w.Dp[e.y >> 16] * w.pg[13 + (e.y & 0x7fff)] +
+                 w.Dp[e.z >> 16] * w.pg[13 + (e.z & 0x7fff)] + w.Dp[e.w >> 16] * w.pg[13 + (e.w & 0x7fff)];
+      float p = w.hs[13 + i] + CHEB_C * (w.pg[13 + i] + nb * w.dg[i]) - by * w.dg[i];
+      w.hs[13 + i] = p; // neighbours read pg in this pass, not hs
+#else
       float nb = w.Dp[e.x >> 16] * w.hs[13 + (e.x & 0x7fff)] + w.Dp[e.y >> 16] * w.hs[13 + (e.y & 0x7fff)] +
                  w.Dp[e.z >> 16] * w.hs[13 + (e.z & 0x7fff)] + w.Dp[e.w >> 16] * w.hs[13 + (e.w & 0x7fff)];
       float p = w.hs[13 + i] + (nb - by) * w.dg[i];
       w.pg[13 + i] = p;
+#endif
       b[0] += g * p; b[1] += g * g; b[2] += p;
       b[3] += mp * ah.x * p; b[4] += mp * ah.y * p; b[5] += mp * ah.z * p;
     }
@@ -962,7 +994,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
       // ---- exact line search: Newton on phi'(alpha)
       float q1 = 0.f, q2 = 0.f, alpha = 0.f, lo = 0.f, hi = -1.f, d0abs = 0.f;
 #pragma unroll 1
-      for (int ls = 0; ls < 8; ls++) {
+      for (int ls = 0; ls < LS_MAX; ls++) {
         float d1 = 0.f, d2 = 0.f;
         PRAGMA_HOT
         for (int c = tid; c < ncon; c += NT) {
@@ -1027,7 +1059,15 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
 #pragma unroll
     for (int k = 0; k < 4; k++) S4[k] = -rd(w.rq, 2 + k) + beta * S4[k];
     PRAGMA_HOT
+#if PREC3
+    for (int i = tid; i < nv; i += NT) {
+      float p = i >= 13 ? w.hs[i] : w.pg[i];
+      w.pg[i] = p;
+      w.s[i] = -p + beta * w.s[i];
+    }
+#else
     for (int i = tid; i < nv; i += NT) w.s[i] = -w.pg[i] + beta * w.s[i];
+#endif
     env_sync();
   }
 
