@@ -23,3 +23,8 @@ print("iters: mean", (hist * np.arange(82)).sum() / tot)
 print("hist:", {i: round(100 * h / tot, 2) for i, h in enumerate(hist) if h})
 print("cum>=: ", {k: round(100 * hist[k:].sum() / tot, 3) for k in (10, 15, 20, 30, 40)})
 print("ncon: mean", nc.mean(), "p50", np.percentile(nc, 50), "p99", np.percentile(nc, 99), "max", nc.max())
+# iterations split by probe contact (is the missing arm<->torso coupling of the preconditioner visible?)
+t = env.get_state()[3].cpu().numpy()
+d = env.diag().cpu().numpy()
+inc = t[:, 30] > 0
+print("in contact: %.3f of envs; iters in contact %.2f, free %.2f; ncon in contact %.1f free %.1f" % (inc.mean(), d[inc, 20].mean(), d[~inc, 20].mean(), d[inc, 22].mean(), d[~inc, 22].mean()))
