@@ -166,7 +166,7 @@ def compute_gae(rewards, values, dones, last_values, gamma, lam):
 
 class PPO:
     def __init__(self, env, n_steps=32, batch_size=None, n_epochs=10, learning_rate=3e-4, gamma=0.99, gae_lambda=0.95, clip_range=0.2,
-                 ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, net_arch=None, seed=0, normalize=True, verbose=0):
+                 ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, net_arch=None, seed=0, normalize=True, verbose=0, cuda_graph=None):
         self.env = env  # BatchedUltrasound
         self.device = env.device
         self.N, self.obs_dim, self.act_dim = env.num_envs, env.obs.shape[1], env.action_dim
@@ -183,7 +183,10 @@ class PPO:
             for p in self.policy.parameters():
                 dist.broadcast(p.data, 0)
         torch.manual_seed(seed + 1000 * (self.rank + 1))
-        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5)
+        # On a CUDA device one minibatch step is replayed as two CUDA graphs (launch bound otherwise: ~100 small kernels per step)
+        self.cuda_graph = (self.device.type == "cuda") if cuda_graph is None else bool(cuda_graph)
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5, capturable=self.cuda_graph)
+        self._graphs = None
         self.norm = VecNormalizeState(self.N, self.obs_dim, self.device, gamma=gamma) if normalize else None
         lo, hi = env.action_spec
         self.act_lo = torch.as_tensor(lo, dtype=torch.float32, device=self.device)
@@ -260,7 +263,91 @@ class PPO:
             g.copy_(flat[off:off + n].view_as(g))
             off += n
 
+    def _minibatch_loss(self, obs, act, old_lp, adv, ret):
+        a = (adv - adv.mean()) / (adv.std() + 1e-8)
+        v, lp, ent = self.policy.evaluate(obs, act)
+        ratio = torch.exp(lp - old_lp)
+        pl = -torch.min(a * ratio, a * torch.clamp(ratio, 1 - self.clip, 1 + self.clip)).mean()
+        vl = ((ret - v) ** 2).mean()
+        loss = pl + self.ent_coef * (-ent.mean()) + self.vf_coef * vl
+        return loss, pl, vl, (old_lp - lp).mean()
+
+    def _capture(self, batch):
+        """Capture one minibatch step as two CUDA graphs sharing a memory pool: A = gather + forward + loss + backward + flat
+        gradient bucket, B = (bucket / world) -> grads, clip, Adam.  Between them the bucket is all-reduced eagerly (NCCL)."""
+        n, B, dev = batch[0].shape[0], self.batch_size, self.device
+        bufs = [torch.empty_like(x) for x in (batch[0], batch[1], batch[3], batch[4], batch[5])]  # obs, act, old_lp, adv, ret
+        for b, x in zip(bufs, (batch[0], batch[1], batch[3], batch[4], batch[5])):
+            b.copy_(x)
+        idx = torch.arange(B, device=dev)
+        params = [p for p in self.policy.parameters()]
+        # the warm-up steps below are real optimiser steps on real data: put parameters and Adam state back afterwards
+        saved_p = [p.detach().clone() for p in params]
+        saved_s = {p: {k: v.clone() for k, v in st.items() if torch.is_tensor(v)} for p, st in self.opt.state.items()}
+        stats = [torch.zeros((), device=dev) for _ in range(3)]
+
+        def part_a():
+            loss, pl, vl, kl = self._minibatch_loss(bufs[0][idx], bufs[1][idx], bufs[2][idx], bufs[3][idx], bufs[4][idx])
+            loss.backward()
+            for t, v in zip(stats, (pl, vl, kl)):
+                t.copy_(v.detach())
+            return torch.cat([p.grad.reshape(-1) for p in params])
+
+        def part_b(flat):
+            if self.world > 1:
+                flat = flat / self.world
+            off = 0
+            for p in params:
+                k = p.numel()
+                p.grad.copy_(flat[off:off + k].view_as(p))
+                off += k
+            nn.utils.clip_grad_norm_(params, self.max_grad_norm, foreach=True)
+            self.opt.step()
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.opt.zero_grad(set_to_none=True)
+                part_b(part_a())
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.opt.zero_grad(set_to_none=True)
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga):
+            flat = part_a()
+        with torch.cuda.graph(gb, pool=ga.pool()):
+            part_b(flat)
+        with torch.no_grad():
+            for p, q in zip(params, saved_p):
+                p.copy_(q)
+            for p, st in self.opt.state.items():
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        v.copy_(saved_s[p][k]) if p in saved_s and k in saved_s[p] else v.zero_()
+        self._graphs = dict(a=ga, b=gb, flat=flat, idx=idx, bufs=bufs, stats=stats, n=n)
+
+    def _train_graphed(self, batch):
+        if self._graphs is None or self._graphs["n"] != batch[0].shape[0]:
+            self._capture(batch)
+        g = self._graphs
+        for b, x in zip(g["bufs"], (batch[0], batch[1], batch[3], batch[4], batch[5])):
+            b.copy_(x)
+        n = g["n"]
+        for _ in range(self.n_epochs):
+            perm = torch.randperm(n, device=self.device)
+            for s in range(0, n - self.batch_size + 1, self.batch_size):
+                g["idx"].copy_(perm[s:s + self.batch_size])
+                g["a"].replay()
+                if self.world > 1:
+                    dist.all_reduce(g["flat"], op=dist.ReduceOp.SUM)
+                g["b"].replay()
+            self._n_updates += 1
+        pl, vl, kl = (float(t) for t in g["stats"])
+        self.last_stats.update(policy_loss=pl, value_loss=vl, approx_kl=kl, n_updates=self._n_updates)
+
     def train(self, batch):
+        if self.cuda_graph:
+            return self._train_graphed(batch)
         obs, act, old_v, old_lp, adv, ret = batch
         n = obs.shape[0]
         pl = vl = kl = torch.zeros((), device=self.device)
