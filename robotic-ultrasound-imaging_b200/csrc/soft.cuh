@@ -35,7 +35,8 @@
 // N = D^-1 W.  PREC3 = 0: second order, D^-1 (I + N).  PREC3 = 1: third order with Chebyshev weights, D^-1 (I + c (N + N^2)),
 // c = 4 / (4 - 3 rho^2): the cubic (1 - x) p(x) = 1 - T3(x / rho) / T3(1 / rho) deviates least from 1 on the spectrum [-rho, rho]
 // of N.  rho ~ 0.7 for this model (sum of a slider's pair D over its diagonal) -> c = 1.6; measured at 4096 envs:
-// second order 0.513 ms, c = 1.0 (plain Neumann) 0.513, 1.4: 0.485, 1.7: 0.483, 2.0: 0.488, 2.4: 0.506, 3.0: 0.578.
+// second order 0.513 ms, c = 1.0 (plain Neumann) 0.513, 1.4: 0.485, 1.7: 0.483, 2.0: 0.488, 2.4: 0.506, 3.0: 0.578;
+// fourth order (three stencil passes, a0 (z0 + z1) + a2 (z2 + z3)): 0.488 ms vs 0.464 for the cubic -- not kept.
 #ifndef PREC3
 #define PREC3 1
 #endif
@@ -44,6 +45,10 @@
 #endif
 #ifndef NORESTART
 #define NORESTART 1 // 1: keep the Polak-Ribiere direction across a preconditioner rebuild (flexible CG: beta uses the previous pg, made with the previous preconditioner) instead of restarting; measured 0.464 ms vs 0.485 ms
+#endif
+#ifndef LS_TOL
+#define LS_TOL 1e-3f // line search: stop when |phi'| has dropped by this factor (1e-5 cost one more evaluation per iteration for
+                     // nothing in fp32: 0.464 ms; 1e-3: 0.431 ms, 1e-2: 0.430 ms, same iteration count)
 #endif
 #ifndef LS_MAX
 #define LS_MAX 8 // evaluations of phi'(alpha) per line search (Newton with bracketing; 1 = one quadratic step, unverified)
@@ -1023,7 +1028,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
           d2 = rd(zl, 1) + q2;
         }
         if (ls == 0) d0abs = fabsf(d1);
-        if (fabsf(d1) <= 1e-5f * d0abs || !(d2 > 0.f)) break;
+        if (fabsf(d1) <= LS_TOL * d0abs || !(d2 > 0.f)) break;
         if (d1 < 0.f) lo = alpha; else hi = alpha;
         float an = alpha - d1 / d2;
         if (hi < 0.f) { if (an <= lo) an = 2.f * alpha + 1e-6f; }
