@@ -159,3 +159,28 @@ def test_shard_range_partitions_the_env_ids():
         assert seen == list(range(total))
     with pytest.raises(ValueError):
         shard_range(8, 3, 2)
+
+
+def test_solver_knobs_reach_the_config():
+    """The device solver's knobs travel through make_config unchanged; the defaults are the documented ones."""
+    c = abi.make_config(8, CC_TRACK, control_freq=500)
+    assert c.solver_iterations == 40 and c.solver_tolerance == pytest.approx(1e-5) and c.precond_rebuilds == 0  # 0 = library default (8)
+    c = abi.make_config(8, CC_TRACK, control_freq=500, solver_iterations=12, solver_tolerance=3e-6, precond_rebuilds=3)
+    assert (c.solver_iterations, c.precond_rebuilds) == (12, 3) and c.solver_tolerance == pytest.approx(3e-6)
+
+
+def test_stencil_degree_fits_the_packed_table():
+    """The device keeps each element's pair stencil as ONE 16-byte record of four packed (pair, sign, neighbour) entries
+    (csrc/common.cuh PartTables::nb4; usim_create rejects anything wider): the shell grid of both torso shapes has degree <= 4,
+    every pair appears in the neighbour lists of both of its ends, and the indices fit the bit fields."""
+    from rui_b200.model import cylinder_torso_params
+    for m in (build_model(), build_model(cylinder_torso_params())):
+        a = m.arrays
+        nbr = np.asarray(a["part_nbr"]).reshape(-1, 6)
+        pairs = np.asarray(a["eq_pairs"]).reshape(-1, 2)
+        npart, npair = nbr.shape[0], pairs.shape[0]
+        assert ((nbr >= 0).sum(1) <= 4).all() and npart <= 272 and npair <= 543  # NPART_MAX, NPAIR_MAX - 1 (the empty slot)
+        assert npart < (1 << 15) and npair < (1 << 15)
+        ends = {(int(i), int(j)) for i, j in pairs} | {(int(j), int(i)) for i, j in pairs}
+        listed = {(i, int(j)) for i in range(npart) for j in nbr[i] if j >= 0}
+        assert listed == ends
