@@ -957,7 +957,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
         if (lane == 0) w.okf = allok;
       }
       env_sync();
-      if (w.okf) break;
+      if (w.okf || attempt == 1) break; // (a second failure keeps the clamped factors: the divergence guard ends such an episode)
 #pragma unroll 1
       for (int c = tid; c < ncon; c += NT) {
         w.sk[0][c] = 0.f; w.sk[1][c] = 0.f; w.sk[2][c] = 0.f; w.sc[0][c] = 0.f; w.sc[1][c] = 0.f; w.sc[2][c] = 0.f;
