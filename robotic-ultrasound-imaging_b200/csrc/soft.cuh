@@ -586,6 +586,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
   }
   env_sync();
 
+  float gnorm = 0.f, rhsn = 0.f, hxn = 0.f; // |grad|, |rhs|, |Hx| of the current iterate
   // ------------------------------------------------------------------ helpers (lambdas over the warp)
   // out = (M + E) in, in ONE pass: the two slider sums of `in` it needs (S4) are produced by whoever produced `in`.
   // With q != nullptr also accumulates q[0] += in.Hx, q[1] += in.out (this lane's share).
@@ -722,17 +723,19 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
   };
   // pg = P^-1 grad  (arm: dense 7x7 Cholesky; torso: arrow with the 6x6 Schur complement, solved with a WORLD-frame angular part).
   // A slider without contacts couples to the free body through m a_i only; the few with contacts add their owner slot's (K a, r x K a).
-  // Lands in w.rp[9] = grad.pg_old and in w.rq: [0] grad.pg, [1] |grad|^2, [2..5] the slider sums of pg (the next S4).
-  auto precond = [&]() {
-    float a[10];
+  // Lands in w.rp: [9] = grad.pg_old, [10] = |grad|^2 (the convergence test: returns false when the solve has converged, before
+  // the solves and the stencil passes) and in w.rq: [0] grad.pg, [2..5] the slider sums of pg (the next S4).
+  auto precond = [&]() -> bool {
+    float a[11];
 #pragma unroll
-    for (int k = 0; k < 10; k++) a[k] = 0.f;
+    for (int k = 0; k < 11; k++) a[k] = 0.f;
     PRAGMA_HOT
     for (int i = tid; i < np; i += NT) {
       float g = w.grad[13 + i], gi = g * w.dg[i];
       v3 ah = xyz(pt.ax4[i]);
       a[0] += ah.x * gi; a[1] += ah.y * gi; a[2] += ah.z * gi;
       a[9] += g * w.pg[13 + i];
+      a[10] += g * g;
       w.hs[13 + i] = gi; // hs is free between the line search and the next applyH
       int cs = w.cslot[i];
       if (cs >= 0) {
@@ -740,9 +743,13 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
         a[6] += w.sc[0][cs] * gi; a[7] += w.sc[1][cs] * gi; a[8] += w.sc[2][cs] * gi;
       }
     }
-    if (tid < 13) a[9] += w.grad[lane] * w.pg[lane];
+    if (tid < 13) { a[9] += w.grad[lane] * w.pg[lane]; a[10] += w.grad[lane] * w.grad[lane]; }
     tsum_to(a, lane, w.rp[wrp]);
     env_sync();
+    // |grad| is known here: a converged solve stops before the solves, the stencil passes and the second reduction
+    // (fp32 floor of the gradient is ~eps * (|Hx| + |rhs|): the terms that cancel in it)
+    gnorm = sqrtf(rd(w.rp, 10));
+    if (gnorm <= dm.tol * (1.f + rhsn + hxn)) return false;
     float gd[13]; // dense part of the gradient
 #pragma unroll
     for (int k = 0; k < 13; k++) gd[k] = w.grad[k];
@@ -765,12 +772,10 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     float b[6] = {0, 0, 0, 0, 0, 0};
     if (tid == 0) {
 #pragma unroll
-      for (int j = 0; j < 7; j++) { w.pg[j] = ya[j]; b[0] += gd[j] * ya[j]; b[1] += gd[j] * gd[j]; }
+      for (int j = 0; j < 7; j++) { w.pg[j] = ya[j]; b[0] += gd[j] * ya[j]; }
       if (dm.soft) {
         w.pg[7] = y[0]; w.pg[8] = y[1]; w.pg[9] = y[2]; w.pg[10] = yb.x; w.pg[11] = yb.y; w.pg[12] = yb.z;
         b[0] += gd[7] * y[0] + gd[8] * y[1] + gd[9] * y[2] + gd[10] * yb.x + gd[11] * yb.y + gd[12] * yb.z;
-#pragma unroll
-        for (int k = 7; k < 13; k++) b[1] += gd[k] * gd[k];
       }
     }
 #if PREC3
@@ -805,11 +810,12 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
       float p = w.hs[13 + i] + (nb - by) * w.dg[i];
       w.pg[13 + i] = p;
 #endif
-      b[0] += g * p; b[1] += g * g; b[2] += p;
+      b[0] += g * p; b[2] += p;
       b[3] += mp * ah.x * p; b[4] += mp * ah.y * p; b[5] += mp * ah.z * p;
     }
     tsum_to(b, lane, w.rq[wrp]);
     env_sync();
+    return true;
   };
 
   // preconditioner from the current active set (contact zones); rebuilt when the zones change.  Runs 1-3 times per solve.
@@ -971,18 +977,14 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
   };
 
   // ------------------------------------------------------------------ K6: nonlinear PCG; pass -1 evaluates the warm start
-  float gpg = 1.f, gnorm = 0.f, rhsn = 0.f, hxn = 0.f;
+  float gpg = 1.f;
   int iters = 0, rebuilds = 0;
   const int maxit = mode == 1 ? 2 * dm.iters : dm.iters;
   // every helper has exactly ONE call site (code size: the loop body must stay inside the instruction cache)
 #pragma unroll 1
   for (int it = -1; it < maxit; it++) {
     const bool init = it < 0;
-    if (!init) {
-      // fp32 floor of the gradient is ~eps * (|Hx| + |rhs|): the terms that cancel in it
-      if (gnorm <= dm.tol * (1.f + rhsn + hxn)) break;
-      iters = it + 1;
-    }
+    iters = it + 1; // iterations that changed x so far (the convergence test sits in precond(), right after the gradient)
     const float* vin = init ? w.x : w.s;
     float* vout = init ? w.Hx : w.hs;
     float q12[2] = {0.f, 0.f};
@@ -1059,9 +1061,8 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
       rebuilds += init ? 0 : 1;
       restart = init || !NORESTART;
     }
-    precond();
+    if (!precond()) break;
     const float gpo = rd(w.rp, 9), gpn = rd(w.rq, 0); // grad.pg with the previous pg (Polak-Ribiere) and with the new one
-    gnorm = sqrtf(rd(w.rq, 1));
     float beta = restart ? 0.f : fmaxf(0.f, (gpn - gpo) / fmaxf(gpg, 1e-30f));
     gpg = gpn;
 #pragma unroll
