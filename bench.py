@@ -34,14 +34,31 @@ ENV_OPTS = dict(controller_configs=RL_CONTROLLER, control_freq=500, horizon=1000
 SEED = 3  # rl_config.yaml:1
 
 
-def ncu_traffic(envs_per_gpu):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (scaled to this launch's env count)."""
+def _ncu_capture():
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
     with open(p) as f:
-        t = json.load(f)
-    return t["dram_bytes_per_launch"] * envs_per_gpu / t["envs_per_launch"]
+        return json.load(f)
+
+
+def ncu_traffic(envs_per_gpu):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (scaled to this launch's env count)."""
+    t = _ncu_capture()
+    return None if t is None else t["dram_bytes_per_launch"] * envs_per_gpu / t["envs_per_launch"]
+
+
+def issue_slots(envs_per_gpu, kernel_ms, sm_mhz, n_sm=148):
+    """The bound that actually applies: warp instructions issued per second against 4 schedulers x SMs x clock.
+    Instruction count per launch from the committed ncu capture (scaled to this launch's env count), time measured live."""
+    t = _ncu_capture()
+    if t is None or "warp_instructions_per_launch" not in t or not sm_mhz:
+        return None
+    inst = t["warp_instructions_per_launch"] * envs_per_gpu / t["envs_per_launch"]
+    achieved = inst / (kernel_ms * 1e-3) / 1e9
+    peak = 4 * n_sm * sm_mhz * 1e6 / 1e9
+    return {"bound": "fp32 issue slots (secondary, informative)", "achieved": achieved, "peak": peak, "unit": "G warp-instr/s",
+            "frac": achieved / peak, "source": "smsp__inst_executed.sum of profiles/r01_ncu_summary.md x live kernel time"}
 
 
 def peaks():
@@ -249,6 +266,9 @@ def run_cuda(args):
                          "traffic": args.traffic if args.traffic is not None else ncu_traffic(per_gpu), "kernel": "solve_kernel", "kernel_ms": kernel_ms, "peak_source": which,
                          "note": "algorithmic bytes 7008 B/env-step (SURVEY 8d); the step is FP32-issue/latency bound, not HBM bound"},
         }
+        iss = issue_slots(per_gpu, kernel_ms, clocks.get("sm_mhz"))
+        if iss is not None:
+            line["issue_slots"] = iss
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             if args.cpu_steps <= 0:  # bounded sample: 10-20 s of CPU work, sized from a short calibration run
