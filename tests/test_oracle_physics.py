@@ -164,3 +164,59 @@ def test_single_soft_contact_closed_form(O):
     f = (aref - Jn @ a0) / (A + R)  # frictionless 1-row solution; friction rows carry ~0 at rest
     assert f > 0
     assert abs(c["force"][0][0] - f) < 2e-3 * f
+
+
+def _cone_force_numpy(j, Dn, Dt, mu, fr):
+    """Elliptic-cone (condim 3) constraint force of MuJoCo's primal problem, written independently of oracle.c: j = (J a - aref) in the
+    contact frame (normal first); returns (force, zone) with zone 0 = top (no force), 1 = middle (on the cone), 2 = bottom (quadratic)."""
+    N, U = j[0] * mu, fr * j[1:]
+    T = np.hypot(*U)
+    if N >= mu * T or (T <= 0 and N >= 0):
+        return np.zeros(3), 0
+    if mu * N + T <= 0 or (T <= 0 and N < 0):
+        return -np.array([Dn * j[0], Dt * j[1], Dt * j[2]]), 2
+    Dm = Dn / (mu * mu * (1 + mu * mu))
+    f0 = -Dm * (N - mu * T) * mu
+    return np.array([f0, -f0 / T * U[0] * fr, -f0 / T * U[1] * fr]), 1
+
+
+def test_friction_cone_solution_satisfies_the_optimality_conditions(O):
+    """One frictional contact (probe tip 1 mm inside the rigid table) with the tip sticking, sliding and separating: the oracle's
+    solution satisfies M (a - a_smooth) = J^T f, and f is the cone force of J a - aref computed by an independent numpy
+    restatement of the elliptic-cone formulas -- in all three zones; when sliding, |f_t| = friction * f_n exactly."""
+    from rui_b200.model import SceneParams
+    pk = abi.PackedModel(build_model(SceneParams(soft_torso=False)))
+    m = pk.model
+    e = O.OracleEnv(pk, _cfg(CC_FIXED), 0)
+    e.reset()
+    q = O.OracleEnv(abi.PackedModel(build_model()), _cfg(CC_TRACK), 0).ik([0.0, 0.0, 0.8 - 0.001])
+    e.set_state(qpos=q, qvel=np.zeros(7))
+    e.forward(np.zeros(7))
+    J0 = e.eef()[0]
+    dmax, tc = 0.95, 0.02
+    K, B = 1 / (dmax ** 2 * tc ** 2), 2 / (dmax * tc)
+    fr = max(m.params.table_friction, m.params.probe_friction)
+    mu = fr / np.sqrt(m.params.impratio)
+    zones = []
+    for twist in ([0.001, 0, 0, 0, 0, 0], [3.0, 0, 0, 0, 0, 0], [0, 0, 2.0, 0, 0, 0]):  # site velocity: creep, fast slide, lift-off
+        qd = np.linalg.pinv(J0) @ np.array(twist, dtype=float)
+        e.set_state(qpos=q, qvel=qd)
+        e.forward(np.zeros(7))
+        c = e.contacts()
+        assert len(c["dist"]) == 1
+        F, f, depth = c["frame"][0], c["force"][0], -c["dist"][0]
+        J, pos, _ = e.eef()
+        Jc = J[:3] + np.cross(J[3:].T, c["pos"][0] - pos).T  # contact-point Jacobian (world), then rows normal / t1 / t2
+        Jf = F @ Jc
+        a, a0, M = e.qacc, e.qacc_smooth, e.M
+        assert np.abs(M @ (a - a0) - Jf.T @ f).max() < 1e-8 * max(1.0, np.abs(f).max())
+        imp = dmax  # penetration >= solimp width
+        v = Jf @ qd
+        aref = np.array([-B * v[0] + K * imp * depth, -B * v[1], -B * v[2]])
+        Dn = 1.0 / ((1 - imp) / imp * m.body_invweight0[m.ids[4], 0])
+        fe, zone = _cone_force_numpy(Jf @ a - aref, Dn, Dn * m.params.impratio, mu, fr)
+        zones.append(zone)
+        assert np.abs(f - fe).max() < 1e-7 * max(1.0, np.abs(fe).max()), (twist, f, fe)
+        if zone == 1:
+            assert abs(np.hypot(f[1], f[2]) / f[0] - fr) < 1e-9
+    assert zones == [2, 1, 0]
