@@ -164,7 +164,6 @@ __device__ __forceinline__ void philox(unsigned k0, unsigned k1, unsigned c0, un
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-__device__ __forceinline__ float u01(unsigned r) { return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
 // ---------------------------------------------------------------- task layer (ultrasound.py, utils/quaternion.py)
 #define GQX (-0.69192486f)
@@ -269,12 +268,4 @@ __device__ __forceinline__ void kbi(float sr0, float sr1, float pos, float* K, f
     *K = -sr0 / (dmax * dmax);
     *B = -sr1 / dmax;
   }
-}
-__device__ __forceinline__ void make_frame(v3 n, v3* t1, v3* t2) {
-  v3 t = (n.y < 0.5f && n.y > -0.5f) ? mk(0, 1, 0) : mk(0, 0, 1);
-  float d = dot(n, t);
-  v3 y = t - d * n;
-  y = (1.f / norm(y)) * y;
-  *t1 = y;
-  *t2 = cross(n, y);
 }

@@ -142,11 +142,6 @@ __device__ __forceinline__ void tma_store_commit_wait() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
-__device__ __forceinline__ float wsum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 // Transposing warp reduction of K values: K-1 shuffles instead of 5K.  Returns, in lane l, the warp total of entry
 // l & (KP-1), KP = K rounded up to a power of two.  Fixed association order -> bit-reproducible.
 template <int K>
