@@ -259,7 +259,8 @@ def run_cuda(args):
                              if flush is not None else "not flushed"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": per_gpu * env.action_dim * 4,
-                    "d2h_bytes_per_step": per_gpu * (19 * 4 * 2 + 4 + 1)},
+                    "d2h_bytes_per_step": per_gpu * (19 * 4 + 4 + 1),
+                    "note": "obs + reward + done every step; terminal observations only for the envs that finished in the step"},
             "gpu_launches": int(launches),
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -161,7 +161,8 @@ int usim_step(usim_handle* h, const float* act_dev, float* obs_dev, float* rew_d
  * inside the call, which synchronises the library's stream.  A buffer that is
  * page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) is the DMA
  * end point itself; a pageable one is staged through the library's pinned
- * memory (one extra host memcpy). */
+ * memory (one extra host memcpy).  tobs_host rows are written only for the envs
+ * whose done flag is set in this step; the other rows are left untouched. */
 int usim_step_host(usim_handle* h, const float* act_host, float* obs_host, float* rew_host,
                    uint8_t* done_host, float* term_obs_host, int auto_reset);
 

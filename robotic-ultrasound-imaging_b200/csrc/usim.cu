@@ -347,12 +347,33 @@ int usim_step_host(usim_handle* h, const float* act, float* obs, float* rew, uin
   CK(cudaMemcpyAsync(o_dst, h->d_obs, N * USIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(r_dst, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(d_dst, h->d_done, N, cudaMemcpyDeviceToHost, s));
-  if (tobs) CK(cudaMemcpyAsync(t_dst, h->d_tobs, N * USIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (obs && o_dst != obs) memcpy(obs, h->h_obs, N * USIM_OBS_DIM * sizeof(float));
   if (rew && r_dst != rew) memcpy(rew, h->h_rew, N * sizeof(float));
   if (done && d_dst != done) memcpy(done, h->h_done, N);
-  if (tobs && t_dst != tobs) memcpy(tobs, h->h_tobs, N * USIM_OBS_DIM * sizeof(float));
+  if (tobs) {
+    // Terminal observations exist only for the envs that finished in this step (typically ~N / episode length of them): fetch those
+    // rows alone; when many envs finish together (a common horizon) one copy of the whole array is cheaper.
+    const size_t row = USIM_OBS_DIM * sizeof(float);
+    size_t ndone = 0;
+    for (size_t e = 0; e < N; e++) ndone += d_dst[e] != 0;
+    if (ndone > 64) {
+      CK(cudaMemcpyAsync(t_dst, h->d_tobs, N * row, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (t_dst != tobs) {
+        for (size_t e = 0; e < N; e++)
+          if (d_dst[e]) memcpy(tobs + e * USIM_OBS_DIM, h->h_tobs + e * USIM_OBS_DIM, row);
+      }
+    } else if (ndone > 0) {
+      for (size_t e = 0; e < N; e++)
+        if (d_dst[e]) CK(cudaMemcpyAsync(t_dst + e * USIM_OBS_DIM, h->d_tobs + e * USIM_OBS_DIM, row, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (t_dst != tobs) {
+        for (size_t e = 0; e < N; e++)
+          if (d_dst[e]) memcpy(tobs + e * USIM_OBS_DIM, h->h_tobs + e * USIM_OBS_DIM, row);
+      }
+    }
+  }
   return 0;
 }
 

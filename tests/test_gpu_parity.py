@@ -460,3 +460,40 @@ def test_host_buffer_call_matches_device_call():
     assert np.array_equal(ho, o.cpu().numpy()) and np.array_equal(hr, r.cpu().numpy()) and np.array_equal(hd, d.cpu().numpy())
     for e in (dev_env, host_env, pin_env):
         e.close()
+
+
+def test_host_buffer_call_fetches_terminal_rows_of_partial_terminations():
+    """Early termination on: a few envs finish in a step.  usim_step_host then fetches only their terminal-observation rows; they
+    equal the device call's, for pageable and page-locked caller buffers, and the other rows of the caller's array stay untouched."""
+    import ctypes as C
+
+    from rui_b200 import _lib
+    opts = dict(seed=21, early_termination=True, torso_solref_randomization=True, initial_probe_pos_randomization=True)
+    N = 64
+    dev_env, host_env, pin_env = (_make(N, True, CC_TRACK, **opts) for _ in range(3))
+    for e in (dev_env, host_env, pin_env):
+        e.reset()
+    rng = np.random.default_rng(9)
+    pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, pin_memory=True).numpy()
+    p_act, p_obs, p_rew, p_done, p_tobs = pin(N, 6), pin(N, 19), pin(N), pin(N, dtype=torch.uint8), pin(N, 19)
+    ho, hr, hd, ht = np.zeros((N, 19), np.float32), np.zeros(N, np.float32), np.zeros(N, np.uint8), np.full((N, 19), -7.0, np.float32)
+    p_tobs[:] = -7.0
+    ptr = lambda x: C.c_void_p(x.ctypes.data)
+    partial = 0
+    touched = np.zeros(N, bool)
+    for s in range(60):
+        a = rng.uniform(0, 1, size=(N, 6)).astype(np.float32)
+        o, r, d, _ = dev_env.step(torch.as_tensor(a), auto_reset=True)
+        tob, dn = dev_env.term_obs.cpu().numpy(), d.cpu().numpy().astype(bool)
+        _lib.check(_lib.lib().usim_step_host(host_env._h, ptr(a), ptr(ho), ptr(hr), ptr(hd), ptr(ht), 1))
+        p_act[:] = a
+        _lib.check(_lib.lib().usim_step_host(pin_env._h, ptr(p_act), ptr(p_obs), ptr(p_rew), ptr(p_done), ptr(p_tobs), 1))
+        partial += 0 < dn.sum() < N
+        touched |= dn
+        for go, gd, gt in ((ho, hd, ht), (p_obs, p_done, p_tobs)):
+            assert np.array_equal(go, o.cpu().numpy()) and np.array_equal(gd.astype(bool), dn), s
+            assert np.array_equal(gt[dn], tob[dn]), s
+            assert (gt[~touched] == -7.0).all(), s  # rows of envs that never finished were never written
+    assert partial >= 3
+    for e in (dev_env, host_env, pin_env):
+        e.close()
