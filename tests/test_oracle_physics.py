@@ -220,3 +220,81 @@ def test_friction_cone_solution_satisfies_the_optimality_conditions(O):
         if zone == 1:
             assert abs(np.hypot(f[1], f[2]) / f[0] - fr) < 1e-9
     assert zones == [2, 1, 0]
+
+
+def test_soft_scene_solution_satisfies_the_optimality_conditions(O, soft_model):
+    """Whole soft scene (probe on the torso, torso on the table: ~60 contacts, 807 equality rows).  The oracle assembles explicit
+    sparse constraint rows over a generic body tree; here the same forces are written in the FORMULATION THE CUDA KERNEL USES
+    (numpy, float64): equality rows as a per-slider stencil (270 "fix", 536 "smooth" pairs with the episode's solrefsmooth, one
+    tendon), contacts as rigid-body point wrenches on the free body (world force, body-frame torque) plus the slider axis component,
+    probe contacts through the site Jacobian.  At the oracle's solution, M (a - a_smooth) equals the sum of those generalized forces
+    to rounding: the two formulations describe the same constrained dynamics."""
+    m = soft_model.model
+    P, A = m.params, m.arrays
+    cfg = _cfg(CC_TRACK, seed=5, torso_solref_randomization=True, initial_probe_pos_randomization=True)
+    e = O.OracleEnv(soft_model, cfg, 0)
+    e.reset()
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        e.step(rng.uniform(0, 1, 6))
+    q, v, _, ts = e.get_state()
+    e.forward(e.tau)
+    a, a0, M = e.qacc, e.qacc_smooth, e.M
+    c = e.contacts()
+    assert len(c["dist"]) > 40 and set(c["geom2"]) == {1, 2}  # table-particle and probe-particle contacts are both present
+
+    def quat2mat(qq):
+        w_, x, y, z = qq / np.linalg.norm(qq)
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w_ * z), 2 * (x * z + w_ * y)],
+                         [2 * (x * y + w_ * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w_ * x)],
+                         [2 * (x * z - w_ * y), 2 * (y * z + w_ * x), 1 - 2 * (x * x + y * y)]])
+
+    dmin, dmax, width, mid, power = P.solimp
+
+    def imped(pos):  # MuJoCo solimp sigmoid
+        x = abs(pos) / width
+        y = 1.0 if x >= 1 else (x ** power / mid ** (power - 1) if x <= mid else 1 - (1 - x) ** power / (1 - mid) ** (power - 1))
+        return min(max(dmin + (0.0 if x == 0 else y) * (dmax - dmin), 1e-4), 0.9999)
+
+    def KB(sr):  # positive solref: (timeconst, dampratio); negative: direct (stiffness, damping)
+        if sr[0] > 0:
+            tc = max(sr[0], 2 * P.timestep)
+            return 1 / (dmax ** 2 * tc ** 2 * sr[1] ** 2), 2 / (dmax * tc)
+        return -sr[0] / dmax ** 2, -sr[1] / dmax
+
+    R, Pt = quat2mat(q[10:14]), q[7:10]
+    ax, iw = np.asarray(A["part_axis"]), np.asarray(A["dof_invweight0"])
+    qs, vs, acc = q[14:], v[13:], a[13:]
+    g = np.zeros(283)
+    K, B = KB(P.solref)
+    for i in range(270):  # "fix" rows
+        imp = imped(qs[i])
+        D = 1 / max(1e-15, (1 - imp) / imp * iw[13 + i])
+        g[13 + i] += -D * (acc[i] - (-B * vs[i] - K * imp * qs[i]))
+    K2, B2 = KB((-ts[abi.TS_STIFFNESS], -ts[abi.TS_DAMPING]))
+    for ia, ib in np.asarray(A["eq_pairs"]):  # "smooth" pair rows
+        pos, vel = qs[ia] - qs[ib], vs[ia] - vs[ib]
+        imp = imped(pos)
+        D = 1 / max(1e-15, (1 - imp) / imp * (iw[13 + ia] + iw[13 + ib]))
+        f = -D * ((acc[ia] - acc[ib]) - (-B2 * vel - K2 * imp * pos))
+        g[13 + ia] += f
+        g[13 + ib] -= f
+    imp = imped(qs.sum())  # tendon row
+    Dt = 1 / max(1e-15, (1 - imp) / imp * float(np.asarray(A["tendon_invweight0"])[0]))
+    g[13:] += -Dt * (acc.sum() - (-B * vs.sum() - K * imp * qs.sum()))
+    J, spos, _ = e.eef()
+    for k in range(len(c["dist"])):  # contacts: +F on geom2, -F on geom1
+        Fw, pos = c["frame"][k].T @ c["force"][k], c["pos"][k]
+        for geom, sgn in ((c["geom2"][k], 1.0), (c["geom1"][k], -1.0)):
+            if geom == 1:    # table: static
+                continue
+            if geom == 2:    # probe: arm dofs through the site Jacobian moved to the contact point
+                g[:7] += sgn * (J[:3] + np.cross(J[3:].T, pos - spos).T).T @ Fw
+            else:            # particle geom - 4: free body (world force, body-frame torque) + its slider
+                i = geom - 4
+                g[7:10] += sgn * Fw
+                g[10:13] += sgn * R.T @ np.cross(pos - Pt, Fw)
+                g[13 + i] += sgn * (R @ ax[i]) @ Fw
+    lhs = M @ (a - a0)
+    assert np.abs(lhs).max() > 1.0
+    assert np.abs(lhs - g).max() < 1e-9 * np.abs(lhs).max()
