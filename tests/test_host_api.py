@@ -184,3 +184,38 @@ def test_stencil_degree_fits_the_packed_table():
         ends = {(int(i), int(j)) for i, j in pairs} | {(int(j), int(i)) for i, j in pairs}
         listed = {(i, int(j)) for i in range(npart) for j in nbr[i] if j >= 0}
         assert listed == ends
+
+
+def test_bench_roofline_helpers_read_the_committed_capture():
+    """bench.py derives `roofline.traffic` and the informative issue-slot object from profiles/traffic.json (the committed ncu capture)."""
+    import json
+
+    import bench
+    t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    assert t["kernel"] == "solve_kernel" and t["envs_per_launch"] == 4096
+    assert bench.ncu_traffic(4096) == pytest.approx(t["dram_bytes_per_launch"]) and bench.ncu_traffic(8192) == pytest.approx(2 * t["dram_bytes_per_launch"])
+    # traffic at or below the algorithmic bytes: the state stays in L2 between steps, nothing is re-read from HBM
+    assert t["dram_bytes_per_launch"] <= 4096 * bench.ALG_BYTES_PER_ENV_STEP
+    iss = bench.issue_slots(4096, 0.43, 1965.0)
+    assert iss["unit"] == "G warp-instr/s" and 0.2 < iss["frac"] < 1.0 and iss["peak"] == pytest.approx(4 * 148 * 1.965)
+    assert bench.issue_slots(4096, 0.43, None) is None
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines kept under profiles/ carry every key of the measurement contract (a stale or hand-edited line would not)."""
+    import json
+    need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+            "data", "config", "clocks", "e2e", "gpu_launches", "roofline"}
+    for name, n in (("r01_bench.json", 1), ("r01_bench_2gpu.json", 2), ("r01_bench_4gpu.json", 4), ("r01_bench_8gpu.json", 8)):
+        d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+        assert need <= set(d), need - set(d)
+        assert d["n_gpus"] == n and d["unit"] == "env-steps/s" and d["higher_is_better"] is True and d["dtype"] == "f32"
+        assert "workload" in d["config"] and d["gpu_launches"] > 0 and d["vs_baseline"] is None
+        assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and 0 < d["e2e"]["value"] <= d["value"]
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and r["frac"] == pytest.approx(r["achieved"] / r["peak"]) and r["kernel"] == "solve_kernel"
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if n == 1:
+            assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] > 0
+    ref = json.loads(open(os.path.join(ROOT, "profiles", "r01_bench_reference_arm.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "port"
