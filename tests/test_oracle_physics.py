@@ -298,3 +298,60 @@ def test_soft_scene_solution_satisfies_the_optimality_conditions(O, soft_model):
     lhs = M @ (a - a0)
     assert np.abs(lhs).max() > 1.0
     assert np.abs(lhs - g).max() < 1e-9 * np.abs(lhs).max()
+
+
+def _osc_numpy(J, M, bias, q, qd, eef_pos, eef_mat, goal_pos, goal_R, kp, kd, q_init, ctrl_lim, uncouple=True):
+    """robosuite OSC_POSE torque with numpy primitives: Lambda = pinv(J M^-1 J^T), decoupled position /
+    orientation wrench, gravity-and-Coriolis compensation, null-space posture term N^T M (10 (q0 - q) - 2 sqrt(10) qd), clip."""
+    eo = 0.5 * sum(np.cross(eef_mat[:, i], goal_R[:, i]) for i in range(3))
+    vel = J @ qd
+    F = np.r_[kp[:3] * (goal_pos - eef_pos) - kd[:3] * vel[:3], kp[3:] * eo - kd[3:] * vel[3:]]
+    Mi = np.linalg.inv(M)
+    Lf, Lp, Lo = np.linalg.pinv(J @ Mi @ J.T), np.linalg.pinv(J[:3] @ Mi @ J[:3].T), np.linalg.pinv(J[3:] @ Mi @ J[3:].T)
+    W = np.r_[Lp @ F[:3], Lo @ F[3:]] if uncouple else Lf @ F
+    N = np.eye(7) - (Mi @ J.T @ Lf) @ J
+    t = J.T @ W + bias + N.T @ (M @ (10 * (q_init - q) - 2 * np.sqrt(10) * qd))
+    return np.clip(t, -ctrl_lim, ctrl_lim)
+
+
+def test_osc_pose_torques_match_numpy_restatement(O, soft_model):
+    """The oracle's OSC_POSE controller (tracking mode: gains from the action, goal = trajectory point + goal quaternion; fixed mode:
+    delta-pose goal with an axis-angle orientation delta) against a numpy restatement built from its own M, bias and site Jacobian."""
+    m = soft_model.model
+    lim = np.asarray(m.params.ctrl_range, dtype=float)
+    rng = np.random.default_rng(3)
+
+    def xyzw2mat(qx):
+        x, y, z, w = np.asarray(qx) / np.linalg.norm(qx)
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                         [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                         [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+    for cc in (CC_TRACK, CC_FIXED):
+        e = O.OracleEnv(soft_model, _cfg(cc, seed=5, torso_solref_randomization=True, initial_probe_pos_randomization=True), 0)
+        e.reset()
+        lo, hi = (0, 1) if cc is CC_TRACK else (-1, 1)
+        for _ in range(7):
+            e.step(rng.uniform(lo, hi, 6))
+        act = rng.uniform(lo, hi, 6)
+        q, v, _, ts = e.get_state()
+        e.forward()  # kinematics at the current state (the controller call below redoes it)
+        J, pos, mat = e.eef()
+        if cc is CC_TRACK:
+            kp = np.clip(act, 0, 1) * 500.0
+            kd = 2 * np.sqrt(kp)
+            goal_pos, goal_R = ts[abi.TS_TRAJ_PT:abi.TS_TRAJ_PT + 3], xyzw2mat(abi.GOAL_QUAT_XYZW)
+        else:
+            kp = np.full(6, float(cc["kp"]))
+            kd = 2 * np.sqrt(kp) * float(cc["damping_ratio"])
+            delta = np.clip(act, -1, 1) * np.array(cc["output_max"])
+            goal_pos = pos + delta[:3]
+            ang = np.linalg.norm(delta[3:])
+            ax_ = delta[3:] / ang
+            Kx = np.array([[0, -ax_[2], ax_[1]], [ax_[2], 0, -ax_[0]], [-ax_[1], ax_[0], 0]])
+            goal_R = (np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx) @ mat  # Rodrigues: R(delta) @ current orientation
+        tau = e.controller(act)
+        M, bias = e.M[:7, :7], e.bias[:7]
+        want = _osc_numpy(J, M, bias, q[:7], v[:7], pos, mat, goal_pos, goal_R, kp, kd, ts[abi.TS_INIT_JOINT:abi.TS_INIT_JOINT + 7], lim)
+        assert np.abs(tau - want).max() < 1e-9 * max(1.0, np.abs(want).max()), (cc["impedance_mode"], tau, want)
+        assert np.abs(want).max() > 0.5
