@@ -355,3 +355,45 @@ def test_osc_pose_torques_match_numpy_restatement(O, soft_model):
         want = _osc_numpy(J, M, bias, q[:7], v[:7], pos, mat, goal_pos, goal_R, kp, kd, ts[abi.TS_INIT_JOINT:abi.TS_INIT_JOINT + 7], lim)
         assert np.abs(tau - want).max() < 1e-9 * max(1.0, np.abs(want).max()), (cc["impedance_mode"], tau, want)
         assert np.abs(want).max() > 0.5
+
+
+def test_narrowphase_matches_brute_force(O, soft_model):
+    """Probe capsule against the 270 particle capsules: the oracle's closed-form segment-segment narrowphase gives the same contact set
+    and penetration depths as a dense sampling of the two segments; table contacts are the capsule end spheres below the table top."""
+    m = soft_model.model
+    A, P = m.arrays, m.params
+    e = O.OracleEnv(soft_model, _cfg(CC_TRACK, seed=5, torso_solref_randomization=True, initial_probe_pos_randomization=True), 0)
+    e.reset()
+    rng = np.random.default_rng(3)
+    for _ in range(30):
+        e.step(rng.uniform(0, 1, 6))
+    q = e.get_state()[0]
+    e.forward(e.tau)
+    _, spos, smat = e.eef()
+    c = e.contacts()
+    w_, x, y, z = q[10:14] / np.linalg.norm(q[10:14])
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w_ * z), 2 * (x * z + w_ * y)],
+                  [2 * (x * y + w_ * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w_ * x)],
+                  [2 * (x * z - w_ * y), 2 * (y * z + w_ * x), 1 - 2 * (x * x + y * y)]])
+    ax, pp, qs, cr, hl = np.asarray(A["part_axis"]), np.asarray(A["part_pos"]), q[14:], P.cap_radius, P.cap_half_len
+    eo = q[7:10] + (pp + (qs - cr)[:, None] * ax) @ R.T              # outer / inner end-sphere centres of every particle capsule
+    ei = q[7:10] + (pp + (qs - cr - 2 * hl)[:, None] * ax) @ R.T
+    seg = np.asarray(A["probe_seg"]).reshape(2, 3)
+    ptip, pback, pr = spos + smat @ seg[0], spos + smat @ seg[1], float(np.asarray(A["probe_radius"])[0])
+    s = np.linspace(0, 1, 401)
+    a_pts = eo[:, None, :] + s[None, :, None] * (ei - eo)[:, None, :]          # [270, 401, 3]
+    b_pts = ptip[None, :] + s[:, None] * (pback - ptip)[None, :]               # [401, 3]
+    d2 = ((a_pts[:, :, None, :] - b_pts[None, None, :, :]) ** 2).sum(-1)       # [270, 401, 401]
+    dist_bf = np.sqrt(d2.reshape(270, -1).min(1)) - cr - pr
+    probe = {int(g1) - 4: float(d) for g1, g2, d in zip(c["geom1"], c["geom2"], c["dist"]) if g2 == 2 and g1 >= 4}
+    assert len(probe) >= 2
+    for i in range(270):
+        if i in probe:
+            assert abs(probe[i] - dist_bf[i]) < 2e-5, (i, probe[i], dist_bf[i])  # sampling error of the brute force
+        else:
+            assert dist_bf[i] > -2e-5, (i, dist_bf[i])
+    # table: one contact per end sphere below the table top (inside the table's footprint), depth = z - radius - table height
+    table = sorted(float(d) for g2, d in zip(c["geom2"], c["dist"]) if g2 == 1)
+    dz = np.r_[eo[:, 2], ei[:, 2]] - cr - P.table_top_z
+    want = sorted(float(d) for d in dz if d < 0)
+    assert len(table) == len(want) and np.allclose(table, want, atol=1e-12)
