@@ -397,3 +397,40 @@ def test_narrowphase_matches_brute_force(O, soft_model):
     dz = np.r_[eo[:, 2], ei[:, 2]] - cr - P.table_top_z
     want = sorted(float(d) for d in dz if d < 0)
     assert len(table) == len(want) and np.allclose(table, want, atol=1e-12)
+
+
+def test_step_is_semi_implicit_euler_of_the_forward_solution(O, soft_model):
+    """One oracle step = controller torque, forward solve, then mj_Euler: (M + h D) a' = M a (implicit joint damping), v += h a',
+    q += h v_new, free-joint quaternion q <- q * exp(h w / 2) with the body-frame angular velocity; qacc_warmstart <- a."""
+    m = soft_model.model
+    cfg = _cfg(CC_TRACK, seed=9, torso_solref_randomization=True, initial_probe_pos_randomization=True)
+    a_env, b_env = O.OracleEnv(soft_model, cfg, 0), O.OracleEnv(soft_model, cfg, 0)
+    rng = np.random.default_rng(4)
+    for e in (a_env, b_env):
+        e.reset()
+    for _ in range(6):
+        act = rng.uniform(0, 1, 6)
+        a_env.step(act)
+        b_env.step(act)
+    act = rng.uniform(0, 1, 6)
+    q, v, _, _ = b_env.get_state()
+    tau = b_env.controller(act)
+    b_env.forward(tau)
+    a, M, h = b_env.qacc, b_env.M, m.params.timestep
+    damp = np.asarray(m.arrays["g_dof_damping"], dtype=float)
+    ap = np.linalg.solve(M + h * np.diag(damp), M @ a)
+    v_new = v + h * ap
+    q_new = q.copy()
+    q_new[:7] += h * v_new[:7]
+    q_new[7:10] += h * v_new[7:10]
+    w3 = v_new[10:13]
+    ang = h * np.linalg.norm(w3)
+    qr = np.r_[np.cos(ang / 2), np.sin(ang / 2) * w3 / np.linalg.norm(w3)]
+    q0 = q[10:14]
+    qq = np.array([q0[0] * qr[0] - q0[1:] @ qr[1:], *(q0[0] * qr[1:] + qr[0] * q0[1:] + np.cross(q0[1:], qr[1:]))])
+    q_new[10:14] = qq / np.linalg.norm(qq)
+    q_new[14:] += h * v_new[13:]
+    a_env.step(act)
+    qa, va, wa, _ = a_env.get_state()
+    assert np.abs(va - v_new).max() < 1e-10 and np.abs(qa - q_new).max() < 1e-12 and np.abs(wa - a).max() < 1e-12
+    assert np.abs(v_new - v).max() > 1e-4  # something moved
