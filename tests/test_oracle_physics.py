@@ -434,3 +434,22 @@ def test_step_is_semi_implicit_euler_of_the_forward_solution(O, soft_model):
     qa, va, wa, _ = a_env.get_state()
     assert np.abs(va - v_new).max() < 1e-10 and np.abs(qa - q_new).max() < 1e-12 and np.abs(wa - a).max() < 1e-12
     assert np.abs(v_new - v).max() > 1e-4  # something moved
+
+
+def test_probe_contact_force_observation_is_the_sum_of_its_contact_forces(O, soft_model):
+    """obs[0:3] (sim.data.cfrc_ext[probe][-3:], ultrasound.py:365) = world-frame sum of the contact forces acting on the probe, i.e.
+    frame^T f of every contact whose second geom is the probe; obs[9] = running mean of its z component - 5 (ultrasound.py:375,546)."""
+    e = O.OracleEnv(soft_model, _cfg(CC_TRACK, seed=9, torso_solref_randomization=True, initial_probe_pos_randomization=True), 0)
+    e.reset()
+    rng = np.random.default_rng(6)
+    fz_mean = e.get_state()[3][abi.TS_FZ_MEAN]
+    seen = 0
+    for _ in range(12):
+        o, _, _ = e.step(rng.uniform(0, 1, 6))
+        c = e.contacts()
+        F = sum((fr.T @ f for fr, f, g2 in zip(c["frame"], c["force"], c["geom2"]) if g2 == 2), np.zeros(3))
+        assert np.abs(o[:3] - F).max() < 1e-9 * max(1.0, np.abs(F).max())
+        fz_mean = 0.1 * F[2] + 0.9 * fz_mean
+        assert abs(o[9] - (fz_mean - 5)) < 1e-9
+        seen += np.abs(F).max() > 1.0
+    assert seen >= 10  # the probe really presses on the torso
