@@ -168,6 +168,25 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def desync(env, acts, gen, preroll):
+    """Steady-state episode mix, independent of --steps / --warmup: every env gets a uniformly random episode phase
+    (MujocoEnv.timestep through usim_set_state), then `preroll` untimed steps (default: one full horizon) are run, so that
+    every env has been through a reset at a uniformly distributed time: the timed window sees resets staggered at ~N / horizon
+    per step and post-reset transients in their natural proportion, as a long RL run does -- not the lock-step start."""
+    import torch
+
+    from rui_b200 import abi
+    env.reset()
+    q, v, w, t = env.get_state()
+    t[:, abi.TS_TIMESTEP] = torch.randint(0, env.horizon, (env.num_envs,), device=t.device, generator=gen).float()
+    env.set_state(task=t)
+    n = env.horizon if preroll < 0 else preroll
+    for i in range(n):
+        env.step(acts[i % len(acts)])
+    torch.cuda.synchronize()
+    return n
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -186,12 +205,12 @@ def run_cuda(args):
     else:
         per_gpu = 4096 if world == 1 else 65536 // world
     env = BatchedUltrasound(per_gpu, device=dev, seed=SEED, env_id_offset=rank * per_gpu, solver_iterations=args.iters, precond_rebuilds=args.rebuilds, **({"solver_tolerance": args.tol} if args.tol else {}), **ENV_OPTS)
-    env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(SEED + rank)
     nact = 8
     acts = [torch.rand(per_gpu, env.action_dim, device=dev, generator=gen) for _ in range(nact)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if not args.no_flush else None
+    preroll = desync(env, acts, gen, args.preroll)
 
     def barrier():
         torch.cuda.synchronize()
@@ -202,6 +221,7 @@ def run_cuda(args):
     # ---------------- device-resident throughput
     for i in range(args.warmup):
         env.step(acts[i % nact])
+    env.set_timing(True)  # CUDA events around the dominant kernel (opt-in: off in production)
     env.kernel_time(reset=True)
     sampler = ClockSampler(local)
     sampler.start()
@@ -221,6 +241,7 @@ def run_cuda(args):
     clocks = sampler.result()
     ms = sum(a.elapsed_time(b) for a, b in evs)
     kms, kn = env.kernel_time(reset=True)
+    env.set_timing(False)
     diag = env.diag()
     mean_ncon, mean_iters = float(diag[:, 22].mean()), float(diag[:, 20].mean())
 
@@ -243,6 +264,31 @@ def run_cuda(args):
     value = total_envs * args.steps / (ms_max * 1e-3)
     e2e = total_envs * args.steps / (e2e_ms_max * 1e-3)
 
+    # N > 1 (config 4: 65536 envs split over the ranks): the honest denominator of a scaling efficiency is ONE GPU running all
+    # 65536 envs, not the 4096-env N=1 line (a smaller batch per GPU has a longer launch tail).  Rank 0 measures it here, with
+    # the same pre-roll and timing, while the other ranks wait.
+    strong_ref = None
+    if world > 1 and not args.no_strong_ref:
+        if rank == 0:
+            env.close()
+            big = BatchedUltrasound(total_envs, device=dev, seed=SEED, env_id_offset=0, solver_iterations=args.iters,
+                                    precond_rebuilds=args.rebuilds, **({"solver_tolerance": args.tol} if args.tol else {}), **ENV_OPTS)
+            bacts = [torch.rand(total_envs, big.action_dim, device=dev, generator=gen) for _ in range(nact)]
+            desync(big, bacts, gen, args.preroll)
+            bev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for i in range(args.steps):
+                if flush is not None:
+                    flush.zero_()
+                bev[i][0].record()
+                big.step(bacts[i % nact])
+                bev[i][1].record()
+            torch.cuda.synchronize()
+            bms = sum(a.elapsed_time(b) for a, b in bev)
+            strong_ref = {"n_gpus": 1, "envs": total_envs, "value": total_envs * args.steps / (bms * 1e-3), "unit": "env-steps/s",
+                          "ms_per_step": bms / args.steps, "note": "same workload on ONE GPU (rank 0), measured in this run"}
+            big.close()
+        barrier()
+
     if rank == 0:
         peak, which = peaks()
         achieved = per_gpu * ALG_BYTES_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e9
@@ -253,7 +299,10 @@ def run_cuda(args):
             "config": {"workload": ("BASELINE config 3: soft-torso sweep task, 4096 envs on 1 B200" if world == 1 and not args.envs else
                                     f"BASELINE config 4: soft-torso sweep task, {total_envs} envs over {world} GPU(s)"),
                        "envs_total": total_envs, "envs_per_gpu": per_gpu, "controller": "OSC_POSE tracking (rl_config.yaml)",
-                       "actions": "U[0,1]^6 (torch.Generator seed 3)", "auto_reset": True, "early_termination": False,
+                       "actions": "U[0,1]^6 (torch.Generator seed 3)", "auto_reset": True,
+                       "early_termination": ENV_OPTS["early_termination"],
+                       "episode_phase": f"uniformly random per env + {preroll} untimed pre-roll steps (steady-state mix of resets and "
+                                        "post-reset transients; independent of --steps/--warmup)",
                        "solver": f"PCG cap {args.iters}, relative gradient tolerance {args.tol or 1e-5:g}", "mean_ncon": mean_ncon, "mean_solver_iters": mean_iters,
                        "l2": "state (~27 MB at 4096 envs) is smaller than L2; 256 MiB memset between steps, outside the per-step events"
                              if flush is not None else "not flushed"},
@@ -267,6 +316,8 @@ def run_cuda(args):
                          "traffic": args.traffic if args.traffic is not None else ncu_traffic(per_gpu), "kernel": "solve_kernel", "kernel_ms": kernel_ms, "peak_source": which,
                          "note": "algorithmic bytes 7008 B/env-step (SURVEY 8d); the step is FP32-issue/latency bound, not HBM bound"},
         }
+        if strong_ref is not None:
+            line["strong_ref"] = strong_ref
         iss = issue_slots(per_gpu, kernel_ms, clocks.get("sm_mhz"))
         if iss is not None:
             line["issue_slots"] = iss
@@ -294,11 +345,16 @@ def main():
     ap.add_argument("--iters", type=int, default=40, help="solver iteration cap")
     ap.add_argument("--rebuilds", type=int, default=0, help="preconditioner rebuilds allowed per solve (0: library default)")
     ap.add_argument("--tol", type=float, default=0.0, help="device solver tolerance (0: library default 1e-5)")
+    ap.add_argument("--preroll", type=int, default=-1, help="untimed steps after randomising the episode phases (-1: one horizon)")
+    ap.add_argument("--early-termination", action="store_true", help="rl_config.yaml:53 (episodes then last tens of steps under random actions)")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-strong-ref", action="store_true", help="N>1: skip the 1-GPU x all-envs reference measurement on rank 0")
     ap.add_argument("--cpu-steps", type=int, default=0, help="env steps per host thread of the cpu_baseline sample (0: ~15 s of CPU work)")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch of the dominant kernel from an ncu capture")
     args = ap.parse_args()
+    if args.early_termination:
+        ENV_OPTS["early_termination"] = True
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -18,6 +18,11 @@
  *   - return 0 = OK, negative = error (message via usim_last_error()).
  *   - one handle per (process, GPU); calls are stream-ordered on the given
  *     stream, not thread-safe, and never synchronise the device unless stated.
+ *     Use ONE stream for the stream-taking calls of a handle (or order your
+ *     streams yourself).  usim_step_host works on a private stream: it waits
+ *     (cudaStreamWaitEvent) for the last usim_reset / usim_step /
+ *     usim_set_state issued on a caller's stream and synchronises its own
+ *     stream before returning, so the two kinds of call may be mixed freely.
  *   - no CPU fallback: usim_create fails if no sm_100-class device is present.
  *   - quaternions are (w,x,y,z) in qpos (MuJoCo), (x,y,z,w) where robosuite
  *     hands them to the task code (obs[15:19]).
@@ -32,7 +37,7 @@
 extern "C" {
 #endif
 
-#define USIM_ABI_VERSION 1
+#define USIM_ABI_VERSION 2
 #define USIM_OBS_DIM 19      /* robot0_proprio-state, ultrasound.py:363-401 */
 #define USIM_TASK_DIM 48     /* per-env task-state record, layout below */
 #define USIM_MAX_ACTION 7
@@ -116,6 +121,8 @@ typedef struct usim_config {
   int32_t uncouple_pos_ori;
   int32_t solver_iterations; /* CG iteration cap per step (device) */
   int32_t precond_rebuilds;   /* preconditioner rebuilds allowed per solve when contact zones change (0: default 8) */
+  int32_t ignore_done;        /* robosuite `ignore_done`: the horizon does not end the episode (early termination still does) */
+  int32_t reserved0;
   uint64_t seed;
   double control_freq;
   double kp[6], damping_ratio[6];      /* fixed mode (rl_config.yaml:39-40) */
@@ -144,9 +151,15 @@ int usim_destroy(usim_handle* h);
 int usim_reset(usim_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream);
 
 /* One control step for every env.  Replaces `MujocoEnv.step(action)` [robosuite]
- * = sim.forward(); Robot.control (OSC_POSE); sim.step(); then
+ * = int(control_timestep / timestep) physics substeps of
+ *   { sim.forward(); Robot.control (OSC_POSE; the goal is set on the first
+ *     substep only); sim.step() }   (1 substep at rl_config.yaml's 500 Hz, 25 at
+ *   the env default of 20 Hz, ultrasound.py:119); then
  * `Ultrasound._post_action` (ultrasound.py:512-550), `reward` (:230-269),
  * `_check_terminated` (:635-670) and the observables (:363-401).
+ * The observation is the one robosuite returns: sampled after the last
+ * sim.step() and BEFORE _post_action updates the task state, so obs[9..14]
+ * (force / velocity statistics, trajectory point) are those reward() used.
  *   act_dev   [num_envs][action_dim] float
  *   obs_dev   [num_envs][19] float        rew_dev [num_envs] float
  *   done_dev  [num_envs] uint8
@@ -199,8 +212,16 @@ int64_t usim_launch_count(const usim_handle* h);
 /* number of env steps whose constraint solve produced a non-finite result; such an env reports done = 1 with finite outputs
  * and is wiped by the next reset (MuJoCo: "bad qacc" auto-reset).  Synchronises the device. */
 int usim_divergence_count(usim_handle* h, int64_t* count);
-/* elapsed device time (ms) of the dominant kernel over its launches since the
- * last call with reset != 0; measured with CUDA events on the launch stream */
+/* number of env steps (physics substeps) in which more than USIM_MAX_CONTACTS contacts were found and the surplus was
+ * dropped (diag[22] holds the uncapped count of the last step).  Synchronises the device. */
+int usim_contact_overflow_count(usim_handle* h, int64_t* count);
+/* physics substeps per control step = int((1 / control_freq) / timestep) */
+int usim_substeps(const usim_handle* h);
+/* Kernel timing is opt-in (off by default: no event traffic in the hot path).  When enabled every launch of the dominant
+ * kernel in usim_step is bracketed by CUDA events on the launch stream (at most 4096 pending pairs are kept). */
+int usim_set_timing(usim_handle* h, int enable);
+/* elapsed device time (ms) of the dominant kernel over its timed launches since the
+ * last call with reset != 0 */
 int usim_kernel_time(usim_handle* h, int reset, double* total_ms, int64_t* launches);
 
 const char* usim_last_error(void);

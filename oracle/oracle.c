@@ -1232,6 +1232,10 @@ void oracle_reset(oracle_env* e, double* obs) {
   write_obs(e, obs);
 }
 
+static void post_action_impl(double* ts, int horizon, int ignore_done, double control_freq, int early_termination, const double* jnt_range,
+                             const double* eef_pos, const double* eef_quat_xyzw, const double* hand_vel, double fz, int in_contact,
+                             const double* qpos7, double* reward, int* done);
+
 int oracle_step(oracle_env* e, const double* action, double* obs, double* reward, int* done) {
   const usim_model* m = e->m;
   const usim_config* c = &e->cfg;
@@ -1251,9 +1255,13 @@ int oracle_step(oracle_env* e, const double* action, double* obs, double* reward
     integrate(e);
   }
   hand_velocity(e);
-  oracle_post_action(ts, c->horizon, c->control_freq, c->early_termination, m->jnt_range, e->eef_pos, e->eef_quat, e->hand_vel,
-                     e->cfrc[2], e->in_contact, e->qpos, reward, done);
+  /* robosuite's MujocoEnv.step samples the observables inside the substep loop (_update_observables, after sim.step) and returns
+     the cached values: the observation of step t is assembled BEFORE _post_action updates the task state, i.e. obs[9..14] carry
+     traj_pt / running means / dFz of step t-1 -- exactly what reward() reads (ultrasound.py:525 before :528-546).  Pinned by the
+     shipped artifacts: every (old_obs, old_reward) row reproduces its reward from its observation (tests/test_task_golden.py). */
   write_obs(e, obs);
+  post_action_impl(ts, c->horizon, c->ignore_done, c->control_freq, c->early_termination, m->jnt_range, e->eef_pos, e->eef_quat,
+                   e->hand_vel, e->cfrc[2], e->in_contact, e->qpos, reward, done);
   return 0;
 }
 
@@ -1262,6 +1270,12 @@ int oracle_step(oracle_env* e, const double* action, double* obs, double* reward
 void oracle_post_action(double* ts, int horizon, double control_freq, int early_termination, const double* jnt_range,
                         const double* eef_pos, const double* eef_quat_xyzw, const double* hand_vel, double fz, int in_contact,
                         const double* qpos7, double* reward, int* done) {
+  post_action_impl(ts, horizon, 0, control_freq, early_termination, jnt_range, eef_pos, eef_quat_xyzw, hand_vel, fz, in_contact, qpos7,
+                   reward, done);
+}
+static void post_action_impl(double* ts, int horizon, int ignore_done, double control_freq, int early_termination, const double* jnt_range,
+                             const double* eef_pos, const double* eef_quat_xyzw, const double* hand_vel, double fz, int in_contact,
+                             const double* qpos7, double* reward, int* done) {
   /* reward first, with the task state of the previous step (:525); the contact query latches has_touched_torso (:733) */
   if (in_contact) ts[USIM_TS_TOUCHED] = 1;
   double pe[2], oe;
@@ -1270,7 +1284,7 @@ void oracle_post_action(double* ts, int horizon, double control_freq, int early_
   ts[USIM_TS_POS_ERR] = pe[0]; ts[USIM_TS_POS_ERR + 1] = pe[1]; ts[USIM_TS_ORI_ERR] = oe;
   ts[USIM_TS_IN_CONTACT] = in_contact;
   double t = ts[USIM_TS_TIMESTEP];
-  int dn = t >= horizon;
+  int dn = t >= horizon && !ignore_done; /* robosuite MujocoEnv._post_action */
   double u = t / (double)horizon + ts[USIM_TS_U0]; /* :528-532, two waypoints; klampt eval clamps ("halt") */
   u = u < 0 ? 0 : (u > 1 ? 1 : u);
   for (int k = 0; k < 3; k++) ts[USIM_TS_TRAJ_PT + k] = ts[USIM_TS_TRAJ_START + k] + u * (ts[USIM_TS_TRAJ_END + k] - ts[USIM_TS_TRAJ_START + k]);
@@ -1394,4 +1408,34 @@ long oracle_rollout(oracle_env** envs, int n, const double* actions, int steps, 
   for (int t = 0; t < threads; t++) { pthread_join(th[t], NULL); total += jobs[t].total; rs += jobs[t].rs; }
   if (reward_sum) *reward_sum = rs;
   return total;
+}
+
+/* one env step of n envs over `threads` host threads, outputs per env (parity tests: the GPU batch is compared step by step).
+ * rc[i] = oracle_step's return (-1: env i was already done, its outputs are left untouched) */
+typedef struct {
+  oracle_env** envs;
+  int n, adim, tid, nthreads;
+  const double* actions;
+  double *obs, *rew;
+  int *done, *rc;
+} stepb_job;
+static void* stepb_worker(void* arg) {
+  stepb_job* j = (stepb_job*)arg;
+  for (int i = j->tid; i < j->n; i += j->nthreads)
+    j->rc[i] = oracle_step(j->envs[i], j->actions + (size_t)i * j->adim, j->obs + (size_t)i * USIM_OBS_DIM, j->rew + i, j->done + i);
+  return NULL;
+}
+void oracle_step_batch(oracle_env** envs, int n, const double* actions, int adim, int threads, double* obs, double* rew, int* done,
+                       int* rc) {
+  if (threads < 1) threads = 1;
+  if (threads > n) threads = n;
+  if (threads > 256) threads = 256;
+  pthread_t th[256];
+  stepb_job jobs[256];
+  for (int t = 0; t < threads; t++) {
+    stepb_job j = {envs, n, adim, t, threads, actions, obs, rew, done, rc};
+    jobs[t] = j;
+    pthread_create(&th[t], NULL, stepb_worker, &jobs[t]);
+  }
+  for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
 }

@@ -80,6 +80,10 @@ void oracle_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_
 long oracle_rollout(oracle_env** envs, int n, const double* actions, int steps, int adim, int auto_reset, int threads,
                     double* reward_sum);
 
+/* one env step of n envs over host threads, per-env outputs: obs [n][19], rew [n], done [n], rc [n] (-1: env already done) */
+void oracle_step_batch(oracle_env** envs, int n, const double* actions, int adim, int threads, double* obs, double* rew, int* done,
+                       int* rc);
+
 #ifdef __cplusplus
 }
 #endif

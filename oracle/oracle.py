@@ -69,6 +69,7 @@ def lib():
         L.oracle_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.oracle_rollout.restype = C.c_long
         L.oracle_rollout.argtypes = [C.POINTER(C.c_void_p), C.c_int, _pd, C.c_int, C.c_int, C.c_int, C.c_int, _pd]
+        L.oracle_step_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, _pd, C.c_int, C.c_int, _pd, _pd, _pi, _pi]
         _lib = L
     return _lib
 
@@ -207,6 +208,20 @@ def rollout(envs, actions, auto_reset=True, threads=1):
     rs = C.c_double()
     tot = lib().oracle_rollout(arr, n, _p(a), steps, adim, int(auto_reset), int(threads), C.byref(rs))
     return tot, rs.value
+
+
+def step_batch(envs, actions, threads=None):
+    """One env step of every env (host threads over envs).  Returns (obs [n,19], rew [n], done [n] bool, stepped [n] bool);
+    envs that were already done are not stepped (stepped[i] = False, outputs zero)."""
+    a = _f64(actions)
+    n, adim = a.shape
+    assert n == len(envs)
+    arr = (C.c_void_p * n)(*[e.h for e in envs])
+    obs, rew = np.zeros((n, OBS_DIM)), np.zeros(n)
+    done, rc = np.zeros(n, np.intc), np.zeros(n, np.intc)
+    lib().oracle_step_batch(arr, n, _p(a), adim, int(threads or os.cpu_count() or 1), _p(obs), _p(rew), done.ctypes.data_as(_pi),
+                            rc.ctypes.data_as(_pi))
+    return obs, rew, done.astype(bool), rc == 0
 
 
 # pure task-layer functions -------------------------------------------------

@@ -33,6 +33,9 @@ SYMBOLS = {
     "usim_action_dim": (C.c_int, [_vp]),
     "usim_launch_count": (C.c_int64, [_vp]),
     "usim_divergence_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "usim_contact_overflow_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "usim_substeps": (C.c_int, [_vp]),
+    "usim_set_timing": (C.c_int, [_vp, C.c_int]),
     "usim_kernel_time": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "usim_last_error": (C.c_char_p, []),
     "usim_abi_version": (C.c_int, []),

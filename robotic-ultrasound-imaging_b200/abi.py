@@ -12,7 +12,7 @@ import numpy as np
 
 from .model import UltrasoundModel
 
-USIM_ABI_VERSION = 1
+USIM_ABI_VERSION = 2
 OBS_DIM = 19
 TASK_DIM = 48
 MAX_CONTACTS = 128
@@ -60,7 +60,7 @@ class UsimConfig(C.Structure):
         ("abi_version", C.c_int32), ("num_envs", C.c_int32), ("env_id_offset", C.c_int32), ("impedance_mode", C.c_int32),
         ("horizon", C.c_int32), ("early_termination", C.c_int32), ("solref_randomization", C.c_int32),
         ("probe_pos_randomization", C.c_int32), ("deterministic_trajectory", C.c_int32), ("uncouple_pos_ori", C.c_int32),
-        ("solver_iterations", C.c_int32), ("precond_rebuilds", C.c_int32),
+        ("solver_iterations", C.c_int32), ("precond_rebuilds", C.c_int32), ("ignore_done", C.c_int32), ("reserved0", C.c_int32),
         ("seed", C.c_uint64),
         ("control_freq", C.c_double),
         ("kp", C.c_double * 6), ("damping_ratio", C.c_double * 6),
@@ -142,6 +142,7 @@ def make_config(
     solver_iterations: int = 40,
     solver_tolerance: float = 1e-5,
     precond_rebuilds: int = 0,
+    ignore_done: bool = False,
     reset_eef_bias=ART_RESET_EEF_BIAS,
 ) -> UsimConfig:
     """Translate the ``suite.make("Ultrasound", ...)`` kwargs (rl_config.yaml:18-57,
@@ -160,6 +161,7 @@ def make_config(
     c.uncouple_pos_ori = int(bool(cc.get("uncouple_pos_ori", True)))
     c.solver_iterations = int(solver_iterations)
     c.precond_rebuilds = int(precond_rebuilds)
+    c.ignore_done = int(bool(ignore_done))
     c.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     c.control_freq = float(control_freq)
     c.kp[:] = _six(cc.get("kp", 150))

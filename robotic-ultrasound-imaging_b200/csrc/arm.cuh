@@ -85,7 +85,8 @@ __device__ __forceinline__ void osc_set_goal(const float* act, const ArmKin& k, 
 // mode: 0 = env step (controller runs), 1 = reset forward (ctrl = 0)
 // mode 0: env step (OSC torques from the action); mode 1: forward pass after a reset (ctrl = 0)
 // (q, qd: the arm joint positions / velocities of this env, in registers: the caller may have just written them to HBM itself)
-__device__ __forceinline__ void arm_forward(int env, int mode, const float (&q)[7], const float (&qd)[7],
+// policy_step: first physics substep of a control step -- the only one on which the OSC goal is set (robosuite Robot.control)
+__device__ __forceinline__ void arm_forward(int env, int mode, bool policy_step, const float (&q)[7], const float (&qd)[7],
                                             const float* __restrict__ act, float* __restrict__ task, float* __restrict__ armbuf) {
   float* ts = task + (size_t)env * USIM_TASK_DIM;
   if (mode == 0 && ts[USIM_TS_DONE] != 0.f) return; // terminated env: frozen until reset
@@ -167,7 +168,7 @@ __device__ __forceinline__ void arm_forward(int env, int mode, const float (&q)[
     const float* a = act + (size_t)env * dm.adim;
     float av[7];
     for (int i = 0; i < dm.adim; i++) av[i] = a[i];
-    osc_set_goal(av, k, ts);
+    if (policy_step) osc_set_goal(av, k, ts);
     float kp[6], kd[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) {
@@ -317,14 +318,14 @@ __device__ __forceinline__ void arm_forward(int env, int mode, const float (&q)[
 // One thread per env.  Also clears `done` (frozen envs report done = 0; the solve kernel sets it for the envs it steps).
 __global__ void __launch_bounds__(64) arm_kernel(int n, const float* __restrict__ qpos, const float* __restrict__ qvel,
                                                  const float* __restrict__ act, float* __restrict__ task, float* __restrict__ armbuf,
-                                                 uint8_t* __restrict__ done) {
+                                                 uint8_t* __restrict__ done, int policy_step) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= n) return;
   if (done) done[env] = 0;
   float q[7], qd[7];
 #pragma unroll
   for (int j = 0; j < 7; j++) { q[j] = qpos[(size_t)env * QPAD + j]; qd[j] = qvel[(size_t)env * QPAD + j]; }
-  arm_forward(env, 0, q, qd, act, task, armbuf);
+  arm_forward(env, 0, policy_step != 0, q, qd, act, task, armbuf);
 }
 
 // ---------------------------------------------------------------- reset (ultrasound.py:416-477, :749-887)
@@ -440,5 +441,5 @@ __global__ void __launch_bounds__(64) reset_kernel(int n, const uint8_t* __restr
 #pragma unroll
   for (int i = 0; i < 9; i++) ts[USIM_TS_GOAL_ORI + i] = k.Rs[i];
   const float qd0[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  arm_forward(env, 1, q, qd0, nullptr, task, armbuf);
+  arm_forward(env, 1, false, q, qd0, nullptr, task, armbuf);
 }

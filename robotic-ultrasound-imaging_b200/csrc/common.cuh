@@ -44,7 +44,7 @@ struct DevModel {
   float top_offset, traj_xr, traj_yr; // trajectory grid on the torso top (ultrasound.py:184-186)
   float rot_I[6];          // constant rotational inertia (xx,yy,zz,xy,xz,yz): capsules about their COM + centre geom
   // config
-  int mode, horizon, early_term, solref_rand, pos_rand, det_traj, uncouple, iters, adim, env_off, nq, nv, max_rebuilds;
+  int mode, horizon, early_term, solref_rand, pos_rand, det_traj, uncouple, iters, adim, env_off, nq, nv, max_rebuilds, ignore_done;
   unsigned seed_lo, seed_hi;
   float ctrl_freq, kp[6], dr[6], in_max, in_min, out_max[6], out_min[6], kp_lim[2], kp_in_max, kp_in_min, tol;
   float eef_bias[3];

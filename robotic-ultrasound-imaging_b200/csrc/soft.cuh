@@ -276,13 +276,14 @@ __device__ __forceinline__ void chol7_solve(const float* L, float* x) {
   }
 }
 
-// mode: 0 = env step, 1 = reset forward (no integration; initialises the running statistics)
+// mode: 0 = env step (last physics substep of a control step: integrates, then the task epilogue), 1 = reset forward (no
+// integration; initialises the running statistics), 2 = intermediate physics substep (integrates, no task epilogue / outputs)
 __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     int n, int mode, const uint8_t* __restrict__ mask, float* __restrict__ qpos, float* __restrict__ qvel, float* __restrict__ warm,
     float* __restrict__ task, const float* __restrict__ armbuf, PartTables pt, const int2* __restrict__ eq_pairs,
     float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
     float* __restrict__ diag, int* __restrict__ ncon_out, int* __restrict__ geom1_out, int* __restrict__ geom2_out,
-    float* __restrict__ dist_out, int* __restrict__ diverged) {
+    float* __restrict__ dist_out, int* __restrict__ counters /* [0] diverged env steps, [1] env steps whose contact list overflowed */) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int env = blockIdx.x;
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
   if (mask && !mask[env]) return;
   WS& w = *reinterpret_cast<WS*>(smem_raw);
   float* ts_g = task + (size_t)env * USIM_TASK_DIM;
-  if (mode == 0 && ts_g[USIM_TS_DONE] != 0.f) return;
+  if (mode != 1 && ts_g[USIM_TS_DONE] != 0.f) return;
   const int np = dm.soft ? dm.npart : 0;
   const int nv = 7 + (dm.soft ? 6 + np : 0);
   const float h = dm.h;
@@ -543,7 +544,10 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     }
   }
   const int ncon_found = ncon;
-  if (ncon > DEV_MAXC) ncon = DEV_MAXC;
+  if (ncon > DEV_MAXC) { // contacts beyond the cap are dropped: counted, never silent (usim_contact_overflow_count)
+    ncon = DEV_MAXC;
+    if (tid == 0 && counters) atomicAdd(counters + 1, 1);
+  }
   env_sync();
 
   // ------------------------------------------------------------------ K5: contact parameters (aref, D)
@@ -1094,7 +1098,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
   in_contact = WPE == 1 ? __any_sync(0xffffffffu, in_contact) : (bool)__syncthreads_or(in_contact);
 
   // ------------------------------------------------------------------ K7: integrate (mj_Euler) and write the state back
-  if (mode == 0) {
+  if (mode != 1) {
     // arm: implicit joint damping, (M + h D) qacc' = M qacc, through a dense 7x7 Cholesky (w.Pa and w.dv are free again)
     if (tid < 7) {
       float s = 0.f;
@@ -1177,7 +1181,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     xnorm2 = rd(w.rq, 0);
   }
   // ------------------------------------------------------------------ K9: task epilogue (lane 0)
-  if (tid == 0) {
+  if (tid == 0 && mode != 2) {
     float* ts = w.ts;
     v3 hv = mk(0, 0, 0);
     {
@@ -1195,12 +1199,19 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     const float* quat_e = w.ab + AB_QUAT;
     float reward = 0.f;
     int dn = 0;
+    // Task-state channels of the observation.  robosuite samples the observables inside the substep loop, BEFORE _post_action
+    // updates the task state, and step() returns the cached values: obs[9..14] of step t carry the task state of step t-1 --
+    // the same values reward() uses.  Pinned by the reference's artifacts: in all 192 (old_obs, old_reward) rows of the shipped
+    // VecNormalize pickles the reward is reproduced from the observation row to 1e-6 (tests/test_task_golden.py).  A reset
+    // force-updates the observables (mode 1: the initialised values below).
+    float o_fz = ts[USIM_TS_FZ_MEAN] - 5.f, o_dfz = ts[USIM_TS_DFZ], o_vel = ts[USIM_TS_VEL_MEAN] - 0.04f;
+    v3 o_tp = ld3(ts + USIM_TS_TRAJ_PT);
     const bool bad = !isfinite(xnorm2) || !isfinite(cfrc.x + cfrc.y + cfrc.z) || !isfinite(ft.x + ft.y + ft.z) || !isfinite(hv.x + hv.y + hv.z) ||
                      !isfinite(eef.x + eef.y + eef.z);
     if (bad) { // keep the outputs finite; the episode ends below and the reset wipes the state
       cfrc = mk(0, 0, 0); ft = mk(0, 0, 0); hv = mk(0, 0, 0);
       if (!isfinite(eef.x + eef.y + eef.z)) eef = ld3(ts + USIM_TS_TRAJ_PT);
-      if (diverged) atomicAdd(diverged, 1);
+      if (counters) atomicAdd(counters, 1);
     }
     if (mode == 0) {
       ts[USIM_TS_TIMESTEP] += 1.f;
@@ -1209,7 +1220,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
       reward = reward_fn(eef, quat_e, ld3(ts + USIM_TS_TRAJ_PT), ts[USIM_TS_VEL_MEAN], ts[USIM_TS_FZ_MEAN], ts[USIM_TS_DFZ], in_contact, pe, &oe);
       ts[USIM_TS_POS_ERR] = pe[0]; ts[USIM_TS_POS_ERR + 1] = pe[1]; ts[USIM_TS_ORI_ERR] = oe;
       float t = ts[USIM_TS_TIMESTEP];
-      dn = t >= (float)dm.horizon;
+      dn = t >= (float)dm.horizon && !dm.ignore_done; // MujocoEnv._post_action: done = timestep >= horizon and not ignore_done
       float u = fminf(fmaxf(t / (float)dm.horizon + ts[USIM_TS_U0], 0.f), 1.f); // ultrasound.py:528-532
 #pragma unroll
       for (int k = 0; k < 3; k++) ts[USIM_TS_TRAJ_PT + k] = ts[USIM_TS_TRAJ_START + k] + u * (ts[USIM_TS_TRAJ_END + k] - ts[USIM_TS_TRAJ_START + k]);
@@ -1236,13 +1247,14 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
       ts[USIM_TS_VEL_MEAN] = norm(hv);   // :474
       ts[USIM_TS_FZ_MEAN] = cfrc.z;      // :477
       ts[USIM_TS_TOUCHED] = 0.f; ts[USIM_TS_TIMESTEP] = 0.f; ts[USIM_TS_DONE] = 0.f;
+      o_fz = ts[USIM_TS_FZ_MEAN] - 5.f; o_dfz = 0.f; o_vel = ts[USIM_TS_VEL_MEAN] - 0.04f;
     }
     ts[USIM_TS_IN_CONTACT] = in_contact ? 1.f : 0.f;
     if (obs) { // ultrasound.py:363-401
       float* o = obs + (size_t)env * USIM_OBS_DIM;
       o[0] = cfrc.x; o[1] = cfrc.y; o[2] = cfrc.z; o[3] = ft.x; o[4] = ft.y; o[5] = ft.z; o[6] = hv.x; o[7] = hv.y; o[8] = hv.z;
-      o[9] = ts[USIM_TS_FZ_MEAN] - 5.f; o[10] = ts[USIM_TS_DFZ]; o[11] = ts[USIM_TS_VEL_MEAN] - 0.04f;
-      o[12] = eef.x - ts[USIM_TS_TRAJ_PT]; o[13] = eef.y - ts[USIM_TS_TRAJ_PT + 1]; o[14] = eef.z - ts[USIM_TS_TRAJ_PT + 2];
+      o[9] = o_fz; o[10] = o_dfz; o[11] = o_vel;
+      o[12] = eef.x - o_tp.x; o[13] = eef.y - o_tp.y; o[14] = eef.z - o_tp.z;
       float gq[4] = {GQX, GQY, GQZ, GQW};
       difference_quat(quat_e, gq, o + 15); // xyzw arrays through a wxyz routine (:390)
     }

@@ -28,13 +28,13 @@ static int fail(const std::string& m) {
   } while (0)
 
 struct usim_handle {
-  int device = 0, n = 0, nq = 0, nv = 0, adim = 6, soft = 0;
+  int device = 0, n = 0, nq = 0, nv = 0, adim = 6, soft = 0, substeps = 1;
   DevModel hm;
   // per-env state, env-major rows (one warp owns one row -> one coalesced 128-B aligned stream)
   float *qpos = nullptr, *qvel = nullptr, *warm = nullptr, *task = nullptr, *armbuf = nullptr, *diag = nullptr;
   int *ncon = nullptr, *geom1 = nullptr, *geom2 = nullptr;
   float* cdist = nullptr;
-  int* diverged = nullptr; // number of env steps that produced a non-finite solution (episode force-ended)
+  int* counters = nullptr; // [0] env steps that produced a non-finite solution (episode force-ended), [1] env steps whose contact list overflowed
   // model tables
   float4 *ax4 = nullptr, *ps4 = nullptr; // (axis, dof_invweight0), (rest position, body_invweight0)
   int4* nb4 = nullptr;                   // packed neighbour / pair stencil
@@ -46,7 +46,8 @@ struct usim_handle {
   uint8_t* d_done = nullptr;
   uint8_t* d_resetmask = nullptr;
   cudaStream_t own_stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_state = nullptr; // recorded on the caller's stream after every state-mutating call: usim_step_host waits on it
+  bool ev_state_valid = false, timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
   int64_t launches = 0, timed_launches = 0;
   double timed_ms = 0.0;
@@ -80,11 +81,14 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail("usim_create: kernels are built for sm_100a only; found sm_" + std::to_string(prop.major * 10 + prop.minor));
   if (m->soft && (m->npart > NPART_MAX || m->npair > NPAIR_MAX)) return fail("usim_create: composite larger than the compiled limits");
+  // physics substeps per control step: int(control_timestep / model_timestep) [robosuite MujocoEnv.step]; 1 at rl_config.yaml's
+  // 500 Hz, 25 at the env's own default of 20 Hz (ultrasound.py:119)
+  if (!(c->control_freq > 0.0)) return fail("usim_create: control_freq must be positive");
   int substeps = (int)((1.0 / c->control_freq) / m->timestep + 1e-9);
-  if (substeps != 1) return fail("usim_create: control_freq must equal 1/timestep (one physics step per control step; rl_config.yaml:26)");
+  if (substeps < 1) return fail("usim_create: control_freq above 1/timestep (less than one physics step per control step)");
 
   usim_handle* h = new usim_handle();
-  h->device = device; h->n = c->num_envs; h->nq = m->nq; h->nv = m->nv; h->soft = m->soft;
+  h->device = device; h->n = c->num_envs; h->nq = m->nq; h->nv = m->nv; h->soft = m->soft; h->substeps = substeps;
   h->adim = c->impedance_mode == USIM_MODE_VARIABLE_Z ? 7 : 6;
   DevModel& d = h->hm;
   memset(&d, 0, sizeof d);
@@ -150,7 +154,7 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
       }
     }
   }
-  d.mode = c->impedance_mode; d.horizon = c->horizon; d.early_term = c->early_termination;
+  d.mode = c->impedance_mode; d.horizon = c->horizon; d.early_term = c->early_termination; d.ignore_done = c->ignore_done;
   d.solref_rand = c->solref_randomization; d.pos_rand = c->probe_pos_randomization; d.det_traj = c->deterministic_trajectory;
   d.uncouple = c->uncouple_pos_ori; d.iters = c->solver_iterations > 0 ? c->solver_iterations : 40;
   d.max_rebuilds = c->precond_rebuilds > 0 ? c->precond_rebuilds : 8; // preconditioner rebuilds per solve when contact zones change
@@ -186,8 +190,8 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   CKH(cudaMemset(h->armbuf, 0, N * ARMBUF * sizeof(float)));
   CKH(cudaMemset(h->diag, 0, N * USIM_DIAG_DIM * sizeof(float)));
   CKH(cudaMemset(h->ncon, 0, N * sizeof(int)));
-  CKH(cudaMalloc((void**)&h->diverged, sizeof(int)));
-  CKH(cudaMemset(h->diverged, 0, sizeof(int)));
+  CKH(cudaMalloc((void**)&h->counters, 2 * sizeof(int)));
+  CKH(cudaMemset(h->counters, 0, 2 * sizeof(int)));
   { // task records: everything zero except DONE = 1 (must reset before stepping)
     std::vector<float> t(N * USIM_TASK_DIM, 0.f);
     for (size_t e = 0; e < N; e++) t[e * USIM_TASK_DIM + USIM_TS_DONE] = 1.f;
@@ -226,6 +230,8 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   CKH(cudaMalloc((void**)&h->d_done, N));
   CKH(cudaMalloc((void**)&h->d_resetmask, N));
   CKH(cudaMemset(h->d_obs, 0, N * USIM_OBS_DIM * sizeof(float)));
+  CKH(cudaMemset(h->d_tobs, 0, N * USIM_OBS_DIM * sizeof(float)));
+  CKH(cudaEventCreateWithFlags(&h->ev_state, cudaEventDisableTiming));
   CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->smem = sizeof(WS);
   if (const char* pad = getenv("USIM_SMEM_PAD")) h->smem += (size_t)atoi(pad); // developer knob: trade resident CTAs for L1 capacity
@@ -241,13 +247,14 @@ int usim_destroy(usim_handle* h) {
   cudaDeviceSynchronize();
   if (g_active == h) g_active = nullptr;
   for (auto& p : h->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-  void* dev[] = {h->diverged, h->qpos, h->qvel, h->warm, h->task, h->armbuf, h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->ax4,
+  void* dev[] = {h->counters, h->qpos, h->qvel, h->warm, h->task, h->armbuf, h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->ax4,
                  h->ps4, h->nb4, h->eq_pairs, h->d_act, h->d_obs, h->d_tobs, h->d_rew,
                  h->d_done, h->d_resetmask};
   for (void* p : dev) if (p) cudaFree(p);
   void* host[] = {h->h_act, h->h_obs, h->h_tobs, h->h_rew, h->h_done};
   for (void* p : host) if (p) cudaFreeHost(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->ev_state) cudaEventDestroy(h->ev_state);
   delete h;
   return 0;
 }
@@ -267,29 +274,41 @@ static int activate(usim_handle* h) {
   return 0;
 }
 
-// forward pass: mode 0 = env step (arm kernel + solve kernel), mode 1 = post-reset forward (solve kernel only: the reset kernel
-// has already run the arm part)
+// state-mutating calls on the caller's stream end with this: the host-buffer entry point (private stream) orders itself after it
+static int mark_state(usim_handle* h, cudaStream_t s) {
+  CK(cudaEventRecord(h->ev_state, s));
+  h->ev_state_valid = true;
+  return 0;
+}
+
+// forward pass: mode 0 = env step (arm kernel + solve kernel; with more than one physics substep per control step the pair is
+// repeated, the OSC goal is set on the first and the task epilogue runs after the last: robosuite MujocoEnv.step), mode 1 = post-reset
+// forward (solve kernel only: the reset kernel has already run the arm part)
 static int launch_forward(usim_handle* h, int mode, const uint8_t* mask, const float* act, float* obs, float* rew, uint8_t* done,
-                          cudaStream_t s, bool timed) {
-  int n = h->n;
-  if (mode == 0) {
-    arm_kernel<<<(n + ARM_BLOCK - 1) / ARM_BLOCK, ARM_BLOCK, 0, s>>>(n, h->qpos, h->qvel, act, h->task, h->armbuf, done);
+                          cudaStream_t s) {
+  const int n = h->n, nsub = mode == 0 ? h->substeps : 1;
+  for (int sub = 0; sub < nsub; sub++) {
+    const bool last = sub == nsub - 1;
+    if (mode == 0) {
+      arm_kernel<<<(n + ARM_BLOCK - 1) / ARM_BLOCK, ARM_BLOCK, 0, s>>>(n, h->qpos, h->qvel, act, h->task, h->armbuf, sub == 0 ? done : nullptr,
+                                                                    sub == 0);
+      h->launches += 1;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool timed = h->timing && mode == 0 && h->pending.size() < 4096; // bounded: the caller drains with usim_kernel_time
+    if (timed) {
+      CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      CK(cudaEventRecord(e0, s));
+    }
+    solve_kernel<<<n, NT, h->smem, s>>>(
+        n, mode == 0 && !last ? 2 : mode, mask, h->qpos, h->qvel, h->warm, h->task, h->armbuf, tables(h), h->eq_pairs, obs, rew, done,
+        h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->counters);
+    if (timed) {
+      CK(cudaEventRecord(e1, s));
+      h->pending.emplace_back(e0, e1);
+    }
     h->launches += 1;
   }
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (timed && h->pending.size() >= 4096) timed = false; // bounded: caller drains with usim_kernel_time
-  if (timed) {
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0, s));
-  }
-  solve_kernel<<<n, NT, h->smem, s>>>(
-      n, mode, mask, h->qpos, h->qvel, h->warm, h->task, h->armbuf, tables(h), h->eq_pairs, obs, rew, done, h->diag,
-      h->ncon, h->geom1, h->geom2, h->cdist, h->diverged);
-  if (timed) {
-    CK(cudaEventRecord(e1, s));
-    h->pending.emplace_back(e0, e1);
-  }
-  h->launches += 1;
   CK(cudaGetLastError());
   return 0;
 }
@@ -301,7 +320,8 @@ int usim_reset(usim_handle* h, const uint8_t* mask_dev, float* obs_dev, void* st
   reset_kernel<<<(h->n + 63) / 64, 64, 0, s>>>(h->n, mask_dev, h->qpos, h->qvel, h->warm, h->task, h->armbuf, nullptr, nullptr);
   h->launches += 1;
   CK(cudaGetLastError());
-  return launch_forward(h, 1, mask_dev, nullptr, obs_dev, nullptr, nullptr, s, false);
+  if (launch_forward(h, 1, mask_dev, nullptr, obs_dev, nullptr, nullptr, s)) return -1;
+  return mark_state(h, s);
 }
 
 // One env step = 4 launches: arm_kernel (also clears `done`), solve_kernel, and for auto-reset reset_kernel (terminal observation,
@@ -312,14 +332,14 @@ int usim_step(usim_handle* h, const float* act_dev, float* obs_dev, float* rew_d
   if (!act_dev || !done_dev) return fail("usim_step: act_dev and done_dev are required");
   if (activate(h)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
-  if (launch_forward(h, 0, nullptr, act_dev, obs_dev, rew_dev, done_dev, s, true)) return -1;
+  if (launch_forward(h, 0, nullptr, act_dev, obs_dev, rew_dev, done_dev, s)) return -1;
   if (auto_reset) {
     reset_kernel<<<(h->n + 63) / 64, 64, 0, s>>>(h->n, done_dev, h->qpos, h->qvel, h->warm, h->task, h->armbuf, obs_dev, term_obs_dev);
     h->launches += 1;
-    if (launch_forward(h, 1, done_dev, nullptr, obs_dev, nullptr, nullptr, s, false)) return -1;
+    if (launch_forward(h, 1, done_dev, nullptr, obs_dev, nullptr, nullptr, s)) return -1;
   }
   CK(cudaGetLastError());
-  return 0;
+  return mark_state(h, s);
 }
 
 // page-locked host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) can be the DMA end point itself
@@ -342,6 +362,9 @@ int usim_step_host(usim_handle* h, const float* act, float* obs, float* rew, uin
   float* r_dst = rew && is_pinned(rew) ? rew : h->h_rew;
   uint8_t* d_dst = done && is_pinned(done) ? done : h->h_done;
   float* t_dst = tobs && is_pinned(tobs) ? tobs : h->h_tobs;
+  // the private stream is ordered after the last state-mutating call made on a caller's stream (usim_reset / usim_step /
+  // usim_set_state), and this call synchronises it before returning: the two kinds of call may be mixed freely
+  if (h->ev_state_valid) CK(cudaStreamWaitEvent(s, h->ev_state, 0));
   CK(cudaMemcpyAsync(h->d_act, a_src, N * h->adim * sizeof(float), cudaMemcpyHostToDevice, s));
   if (usim_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, tobs ? h->d_tobs : nullptr, auto_reset, s)) return -1;
   CK(cudaMemcpyAsync(o_dst, h->d_obs, N * USIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -353,17 +376,16 @@ int usim_step_host(usim_handle* h, const float* act, float* obs, float* rew, uin
   if (done && d_dst != done) memcpy(done, h->h_done, N);
   if (tobs) {
     // Terminal observations exist only for the envs that finished in this step (typically ~N / episode length of them): fetch those
-    // rows alone; when many envs finish together (a common horizon) one copy of the whole array is cheaper.
+    // rows alone; when many envs finish together (a common horizon) one copy of the whole array into the library's staging buffer
+    // is cheaper.  Either way ONLY the rows of finished envs are written into the caller's array.
     const size_t row = USIM_OBS_DIM * sizeof(float);
     size_t ndone = 0;
     for (size_t e = 0; e < N; e++) ndone += d_dst[e] != 0;
     if (ndone > 64) {
-      CK(cudaMemcpyAsync(t_dst, h->d_tobs, N * row, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(h->h_tobs, h->d_tobs, N * row, cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
-      if (t_dst != tobs) {
-        for (size_t e = 0; e < N; e++)
-          if (d_dst[e]) memcpy(tobs + e * USIM_OBS_DIM, h->h_tobs + e * USIM_OBS_DIM, row);
-      }
+      for (size_t e = 0; e < N; e++)
+        if (d_dst[e]) memcpy(tobs + e * USIM_OBS_DIM, h->h_tobs + e * USIM_OBS_DIM, row);
     } else if (ndone > 0) {
       for (size_t e = 0; e < N; e++)
         if (d_dst[e]) CK(cudaMemcpyAsync(t_dst + e * USIM_OBS_DIM, h->d_tobs + e * USIM_OBS_DIM, row, cudaMemcpyDeviceToHost, s));
@@ -410,7 +432,7 @@ int usim_set_state(usim_handle* h, const float* qpos, const float* qvel, const f
   if (warm) rc(h, h->nv, h->nv, QPAD, warm, h->warm, s);
   if (task) rc(h, USIM_TASK_DIM, USIM_TASK_DIM, USIM_TASK_DIM, task, h->task, s);
   CK(cudaGetLastError());
-  return 0;
+  return mark_state(h, s);
 }
 
 int usim_get_contacts(usim_handle* h, int32_t* ncon, int32_t* g1, int32_t* g2, float* dist, void* stream) {
@@ -437,8 +459,21 @@ int64_t usim_launch_count(const usim_handle* h) { return h ? h->launches : -1; }
 int usim_divergence_count(usim_handle* h, int64_t* count) {
   if (!h || !count) return fail("usim_divergence_count: null argument");
   int c = 0;
-  CK(cudaMemcpy(&c, h->diverged, sizeof(int), cudaMemcpyDeviceToHost)); // synchronises the device
+  CK(cudaMemcpy(&c, h->counters, sizeof(int), cudaMemcpyDeviceToHost)); // synchronises the device
   *count = c;
+  return 0;
+}
+int usim_contact_overflow_count(usim_handle* h, int64_t* count) {
+  if (!h || !count) return fail("usim_contact_overflow_count: null argument");
+  int c = 0;
+  CK(cudaMemcpy(&c, h->counters + 1, sizeof(int), cudaMemcpyDeviceToHost)); // synchronises the device
+  *count = c;
+  return 0;
+}
+int usim_substeps(const usim_handle* h) { return h ? h->substeps : -1; }
+int usim_set_timing(usim_handle* h, int enable) {
+  if (!h) return fail("usim_set_timing: null handle");
+  h->timing = enable != 0;
   return 0;
 }
 

@@ -209,6 +209,21 @@ class BatchedUltrasound:
         _lib.check(_lib.lib().usim_divergence_count(self._h, C.byref(c)))
         return int(c.value)
 
+    @property
+    def contact_overflow_count(self) -> int:
+        """env steps in which more than MAX_CONTACTS contacts were found (the surplus is dropped, never silently)."""
+        c = C.c_int64()
+        _lib.check(_lib.lib().usim_contact_overflow_count(self._h, C.byref(c)))
+        return int(c.value)
+
+    @property
+    def substeps(self) -> int:
+        return int(_lib.lib().usim_substeps(self._h))
+
+    def set_timing(self, enable: bool = True):
+        """Opt in to per-launch CUDA-event timing of the dominant kernel (read with :meth:`kernel_time`)."""
+        _lib.check(_lib.lib().usim_set_timing(self._h, int(enable)))
+
     def kernel_time(self, reset: bool = True):
         ms, n = C.c_double(), C.c_int64()
         _lib.check(_lib.lib().usim_kernel_time(self._h, int(reset), C.byref(ms), C.byref(n)))
@@ -218,14 +233,69 @@ class BatchedUltrasound:
 # ----------------------------------------------------------------------------
 # robosuite-style single env
 # ----------------------------------------------------------------------------
-class _Robot:
-    """The slice of robosuite's robot object the task code reads."""
+class _Controller:
+    """``robots[0].controller`` as the task code uses it (ultrasound.py:451-465,535): name, trajectory goal, null-space reference."""
+
+    name = "OSC_POSE"
 
     def __init__(self, env: "Ultrasound"):
         self._env = env
-        self.name = "Panda"
+
+    @property
+    def traj_pos(self):
+        from .abi import TS_TRAJ_PT
+        return self._env._task_state()[TS_TRAJ_PT:TS_TRAJ_PT + 3]
+
+    @property
+    def traj_ori(self):
+        """axis-angle of ``goal_quat`` (T.quat2axisangle, ultrasound.py:456)"""
+        from .abi import GOAL_QUAT_XYZW
+        q = np.asarray(GOAL_QUAT_XYZW, dtype=np.float64)
+        w = float(np.clip(q[3], -1.0, 1.0))
+        den = np.sqrt(1.0 - w * w)
+        return np.zeros(3) if den < 1e-12 else q[:3] * 2.0 * np.arccos(w) / den
+
+    @property
+    def initial_joint(self):
+        from .abi import TS_INIT_JOINT
+        return self._env._task_state()[TS_INIT_JOINT:TS_INIT_JOINT + 7]
+
+    def update_initial_joints(self, q):
+        """ultrasound.py:465: new null-space reference; the OSC goal is re-initialised at the current eef pose by the next reset forward."""
+        from .abi import TS_INIT_JOINT
+        t = self._env.core.get_state()[3]
+        t[0, TS_INIT_JOINT:TS_INIT_JOINT + 7] = torch.as_tensor(np.asarray(q, dtype=np.float32), device=t.device)
+        self._env.core.set_state(task=t)
+
+
+class _RobotModel:
+    """``robots[0].robot_model`` constants the task code reads (ultrasound.py:279-280,346,858-859)."""
+
+    naming_prefix = "robot0_"
+    top_offset = np.array((0.0, 0.0, 1.0))
+    base_xpos_offset = {"table": lambda table_length: (-0.16 - table_length / 2, 0, 0), "bins": (-0.5, -0.1, 0), "empty": (-0.6, 0, 0)}
+
+
+class _Gripper:
+    """``robots[0].gripper`` (ultrasound_probe_gripper.py:26-29, .xml:6-8)."""
+
+    naming_prefix = "gripper0_"
+    root_body = "gripper0_gripper_base"
+    contact_geoms = ["gripper0_probe_collision"]
+    important_geoms = {"probe": ["gripper0_probe_collision"]}
+
+
+class _Robot:
+    """The slice of robosuite's robot object the task code reads (last row)."""
+
+    def __init__(self, env: "Ultrasound"):
+        self._env = env
+        self.name = env.robot_name
         self.dof = 7
         self.init_qpos = np.array(env.core.model.params.init_qpos)
+        self.controller = _Controller(env)
+        self.robot_model = _RobotModel()
+        self.gripper = _Gripper()
 
     @property
     def action_dim(self):
@@ -236,12 +306,37 @@ class _Robot:
         return self._env.core.get_state()[0][0, :7].cpu().numpy().astype(np.float64)
 
     @property
+    def _joint_velocities(self):
+        return self._env.core.get_state()[1][0, :7].cpu().numpy().astype(np.float64)
+
+    @property
     def torques(self):
         return self._env.core.diag()[0, 13:20].cpu().numpy().astype(np.float64)
 
     @property
     def ee_torque(self):
         return self._env.core.diag()[0, 3:6].cpu().numpy().astype(np.float64)
+
+    @property
+    def ee_force(self):
+        return self._env.core.diag()[0, 0:3].cpu().numpy().astype(np.float64)
+
+    @property
+    def _hand_vel(self):
+        """linear eef velocity of the last step (ultrasound.py:373,474,538)"""
+        return self._env.core.obs[0, 6:9].cpu().numpy().astype(np.float64)
+
+    def check_q_limits(self) -> bool:
+        """robosuite ``Robot.check_q_limits``: any joint within 0.1 rad of a limit (ultrasound.py:651)."""
+        q = self._joint_positions
+        rng = np.asarray(self._env.core.model.g_jnt_range, dtype=np.float64)[:7]
+        return bool(np.any(~((rng[:, 0] + 0.1 < q) & (q < rng[:, 1] - 0.1))))
+
+    def set_robot_joint_positions(self, jpos):
+        """ultrasound.py:462: overwrite the arm joint positions (velocities are left as they are, as in robosuite)."""
+        q = self._env.core.get_state()[0]
+        q[0, :7] = torch.as_tensor(np.asarray(jpos, dtype=np.float32), device=q.device)
+        self._env.core.set_state(qpos=q)
 
 
 class Ultrasound:
@@ -284,11 +379,24 @@ class Ultrasound:
         seed=0,
         device=0,
         soft_torso=True,
+        scene_params=None,
     ):
         assert gripper_types == "UltrasoundProbeGripper", "Tried to specify gripper other than UltrasoundProbeGripper in Ultrasound environment!"
-        assert robots == "Panda", "Only the Panda arm is built in this round (UR5e: SURVEY §8f rank 2)"
+        if isinstance(robots, (list, tuple)):
+            assert len(robots) == 1, "Ultrasound is a single-arm env"
+            robots = robots[0]
+        assert robots in ("Panda", "UR5e"), "Robot must be either Panda or UR5e!"  # ultrasound.py:137
         if use_camera_obs or has_renderer or has_offscreen_renderer:
             raise NotImplementedError("rendering / camera observations are out of scope of the hot path (SURVEY §2.1 #4, §8f rank 4)")
+        # kwargs the reference stores but never uses are accepted and ignored exactly as there: table_friction (never forwarded,
+        # ultrasound.py:107,283), initialization_noise (forced to None, :211), reward_scale / reward_shaping (unused by reward()),
+        # placement_initializer (overwritten, :304).  Those that WOULD change the scene are refused instead of silently dropped:
+        if tuple(table_full_size) != (0.8, 0.8, 0.05):
+            raise NotImplementedError("table_full_size other than (0.8, 0.8, 0.05): the arm base offset and the IK frame conversion "
+                                      "(ultrasound.py:279,858) are compiled for the reference's table")
+        if not hard_reset:
+            raise NotImplementedError("hard_reset=False: the device reset always re-draws the torso solref (hard-reset semantics, ultrasound.py:122,291-297)")
+        self.robot_name = robots
         self.save_data = bool(save_data)
         self.use_camera_obs, self.use_object_obs = use_camera_obs, use_object_obs
         self.reward_scale, self.reward_shaping = reward_scale, reward_shaping
@@ -296,11 +404,17 @@ class Ultrasound:
         self.control_timestep = 1.0 / control_freq
         self.ignore_done = ignore_done
         self.early_termination = early_termination
+        self.table_full_size = tuple(table_full_size)
+        if scene_params is None and not use_box_torso:
+            scene_params = cylinder_torso_params(soft_torso=soft_torso)
+        if robots == "UR5e":
+            raise NotImplementedError("UR5e (ultrasound.py:137,833-839): the kernels are specialised for the 7-DoF Panda chain; "
+                                      "SURVEY §8f rank 2, DESIGN.md §9")
         self.core = BatchedUltrasound(
             1, device=device, soft_torso=soft_torso, controller_configs=controller_configs, control_freq=control_freq,
             horizon=horizon, early_termination=early_termination, torso_solref_randomization=torso_solref_randomization,
             initial_probe_pos_randomization=initial_probe_pos_randomization, deterministic_trajectory=deterministic_trajectory,
-            seed=seed, scene_params=None if use_box_torso else cylinder_torso_params(soft_torso=soft_torso))
+            seed=seed, ignore_done=ignore_done, scene_params=scene_params)
         self.robots = [_Robot(self)]
         self.timestep = 0
         self.done = True
@@ -335,7 +449,7 @@ class Ultrasound:
         a = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, -1))
         obs, rew, done, _ = self.core.step(a, auto_reset=False)
         self.timestep += 1
-        d = bool(done[0].item()) and not self.ignore_done
+        d = bool(done[0].item())  # with ignore_done the device does not end the episode at the horizon (early termination still does)
         self.done = d
         flat = obs[0].cpu().numpy().astype(np.float64)
         if self.save_data:
@@ -399,6 +513,42 @@ class Ultrasound:
             idx += 1
             path = os.path.join(fldr, filename + "_" + str(idx) + ".csv")
         pd.DataFrame(data).to_csv(path, header=None, index=None)
+
+    @property
+    def _eef_xpos(self):
+        return self.core.diag()[0, 6:9].cpu().numpy().astype(np.float64)
+
+    @property
+    def _eef_xquat(self):
+        """(x, y, z, w), w >= 0 (robosuite mat2quat)"""
+        return self.core.diag()[0, 9:13].cpu().numpy().astype(np.float64)
+
+    @property
+    def _torso_xpos(self):
+        """ultrasound.py:913-921: world position of the torso root body"""
+        q = self.core.get_state()[0][0].cpu().numpy().astype(np.float64)
+        return q[7:10] if self.core.model.params.soft_torso else np.array([0.0, 0.0, 0.8 + 0.005 + 0.0522])
+
+    def check_contact(self, geoms_1, geoms_2=None) -> bool:
+        """robosuite ``MujocoEnv.check_contact`` on geom names / models with ``contact_geoms`` (ultrasound.py:746)."""
+        def names(g):
+            if g is None:
+                return None
+            if isinstance(g, str):
+                return {g}
+            return set(getattr(g, "contact_geoms", g))
+        a, b = names(geoms_1), names(geoms_2)
+        ncon, g1, g2, _ = self.core.contacts()
+        n, m = int(ncon[0].item()), self.core.model
+        for x, y in zip(g1[0, :n].tolist(), g2[0, :n].tolist()):
+            nx, ny = m.geom_name(x), m.geom_name(y)
+            if (nx in a and (b is None or ny in b)) or (ny in a and (b is None or nx in b)):
+                return True
+        return False
+
+    def _check_probe_contact_with_table(self) -> bool:
+        """ultrasound.py:739-746"""
+        return self.check_contact(self.robots[0].gripper, "table_collision")
 
     def _check_probe_contact_with_torso(self) -> bool:
         """ultrasound.py:714-736: any active contact between probe_collision and a geom named G\\d+_\\d+_\\d+."""

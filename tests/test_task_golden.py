@@ -122,3 +122,48 @@ def test_cylinder_torso_constants(golden):
     assert np.hypot(pos[:, 0], pos[:, 1]).max() <= 0.14 + 1e-12  # (x, y) inside the L2 ball of the largest half extent
     assert abs(np.abs(pos[:, 2]).max() - 0.175) < 1e-12
     assert abs(p.torso_pos[2] - (0.8 + 0.005 + 0.05)) < 1e-12
+
+
+def _reward_from_obs_row(O, o, in_contact):
+    """reward() (ultrasound.py:230-269) evaluated from ONE 19-float observation row: the eef quaternion is recovered from
+    obs[15:19] = difference_quat(eef_xquat, goal_quat) (xyzw arrays through the wxyz routine, :390 -> eef = obs ⊗ goal for unit goal)."""
+    g = np.asarray(abi.GOAL_QUAT_XYZW, dtype=np.float64)
+    g = g / np.linalg.norm(g)
+    a, b = np.asarray(o[15:19], dtype=np.float64), g
+    eef_xyzw = np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                         a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+    # eef_pos - traj_pt = obs[12:15]: only the difference enters the reward
+    r, _, _ = O.reward(o[12:15], eef_xyzw, np.zeros(3), o[11] + 0.04, o[9] + 5.0, o[10], in_contact)
+    return r
+
+
+def test_art_reward_is_reproduced_by_its_observation_row(art, O):
+    """Reference-produced pin of the OBSERVATION TIMING.  The shipped VecNormalize pickles hold the last raw (obs, reward) batch of
+    training (`old_obs`, `old_reward`, 64 envs x 3 models).  reward() at step t reads the task state of step t-1 (ultrasound.py:525
+    runs before :528-546).  In every one of the 192 rows the reward is reproduced, to float32 round-off, from the SAME step's
+    observation row -- so the observation returned for step t also carries the t-1 task state (traj_pt, running means, dFz):
+    robosuite samples the observables inside the substep loop, before _post_action, and returns the cached values.  The oracle
+    and the CUDA kernel follow that (oracle_step: write_obs before post_action; soft.cuh K9)."""
+    n = 0
+    for name, a in art.items():
+        obs, rew = np.array(a["old_obs"]), np.array(a["old_reward"])
+        assert obs.shape == (64, 19) and rew.shape == (64,)
+        for o, r in zip(obs, rew):
+            with_c, without_c = _reward_from_obs_row(O, o, True), _reward_from_obs_row(O, o, False)
+            err = min(abs(r - with_c), abs(r - without_c))  # in_contact itself is not an observation channel
+            assert err < 2e-5, (name, r, with_c, without_c)
+            n += 1
+    assert n == 192
+
+
+def test_oracle_step_returns_the_observation_reward_was_computed_from(O, soft_model):
+    """The same identity on the oracle's own rollouts: reward_t == reward(obs_t) with the step's contact flag."""
+    from conftest import CC_TRACK
+    e = O.OracleEnv(soft_model, abi.make_config(1, CC_TRACK, control_freq=500, seed=5, torso_solref_randomization=True,
+                                                initial_probe_pos_randomization=True), 0)
+    e.reset()
+    rng = np.random.default_rng(1)
+    for s in range(25):
+        o, r, d = e.step(rng.uniform(0, 1, 6))
+        inc = bool(e.get_state()[3][abi.TS_IN_CONTACT])
+        assert abs(r - _reward_from_obs_row(O, o, inc)) < 2e-5, s  # (acos near -1 amplifies the 1e-8 norm error of the 8-digit goal_quat)
