@@ -86,11 +86,10 @@ __device__ __forceinline__ void osc_set_goal(const float* act, const ArmKin& k, 
 // mode 0: env step (OSC torques from the action); mode 1: forward pass after a reset (ctrl = 0)
 // (q, qd: the arm joint positions / velocities of this env, in registers: the caller may have just written them to HBM itself)
 // policy_step: first physics substep of a control step -- the only one on which the OSC goal is set (robosuite Robot.control)
-__device__ __forceinline__ void arm_forward(int env, int mode, bool policy_step, const float (&q)[7], const float (&qd)[7],
-                                            const float* __restrict__ act, float* __restrict__ task, float* __restrict__ armbuf) {
-  float* ts = task + (size_t)env * USIM_TASK_DIM;
+// ts / ab: the env's task record and arm record; act: the env's action row
+__device__ __forceinline__ void arm_forward(int mode, bool policy_step, const float (&q)[7], const float (&qd)[7],
+                                            const float* __restrict__ act, float* __restrict__ ts, float* __restrict__ ab) {
   if (mode == 0 && ts[USIM_TS_DONE] != 0.f) return; // terminated env: frozen until reset
-  float* ab = armbuf + (size_t)env * ARMBUF;
 
   ArmKin k;
   arm_fk(q, k);
@@ -160,14 +159,15 @@ __device__ __forceinline__ void arm_forward(int env, int mode, bool policy_step,
   arm_jac(k, k.hand, Jh);
 
   // ---------------- OSC_POSE torques [SURVEY App. C.2/C.3]
-  float tau[7];
+  float tau[7], dx[7];
+#pragma unroll
+  for (int j = 0; j < 7; j++) dx[j] = 0.f;
   if (mode == 1) {
 #pragma unroll
     for (int j = 0; j < 7; j++) tau[j] = 0.f;
   } else {
-    const float* a = act + (size_t)env * dm.adim;
     float av[7];
-    for (int i = 0; i < dm.adim; i++) av[i] = a[i];
+    for (int i = 0; i < dm.adim; i++) av[i] = act[i];
     if (policy_step) osc_set_goal(av, k, ts);
     float kp[6], kd[6];
 #pragma unroll
@@ -273,6 +273,13 @@ __device__ __forceinline__ void arm_forward(int env, int mode, bool policy_step,
       for (int r = 0; r < 6; r++) s += J[r * 7 + j] * (W[r] - t6[r]);
       tau[j] = fminf(fmaxf(s, -dm.ctrl[j]), dm.ctrl[j]);
     }
+    // warm-start shift for the solve kernel: M^-1 (qfrc_smooth - qfrc_smooth of the previous physics step).  The arm record still
+    // holds the previous step's values here; on the first step of an episode it is stale (the warm start is zero then anyway).
+    if (!(policy_step && ts[USIM_TS_TIMESTEP] == 0.f)) {
+#pragma unroll
+      for (int j = 0; j < 7; j++) dx[j] = tau[j] - bias[j] - dm.arm_damp * qd[j] - ab[AB_QS + j];
+      chol_solve<7>(L, dx);
+    }
   }
 
   // ---------------- F/T sensor pieces for the probe body (welded to link 7)
@@ -313,37 +320,70 @@ __device__ __forceinline__ void arm_forward(int env, int mode, bool policy_step,
   float qx[4];
   mat2quat_xyzw(k.Rs, qx);
   ab[AB_QUAT] = qx[0]; ab[AB_QUAT + 1] = qx[1]; ab[AB_QUAT + 2] = qx[2]; ab[AB_QUAT + 3] = qx[3];
+#pragma unroll
+  for (int j = 0; j < 7; j++) ab[AB_DX + j] = dx[j];
 }
 
-// One thread per env.  Also clears `done` (frozen envs report done = 0; the solve kernel sets it for the envs it steps).
+// One thread per env.  Also clears `done` (frozen envs report done = 0; the solve kernel sets it for the envs it steps), and flattens
+// the iteration-count bins the previous solve launch filled into the launch order of the next one (highest bin first; soft.cuh NBIN).
 __global__ void __launch_bounds__(64) arm_kernel(int n, const float* __restrict__ qpos, const float* __restrict__ qvel,
                                                  const float* __restrict__ act, float* __restrict__ task, float* __restrict__ armbuf,
-                                                 uint8_t* __restrict__ done, int policy_step) {
+                                                 uint8_t* __restrict__ done, int policy_step, int nbin, const int* __restrict__ bin_cnt_prev,
+                                                 const int* __restrict__ bin_items_prev, int* __restrict__ bin_cnt_next,
+                                                 int* __restrict__ order) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= n) return;
+  if (order) {
+    int off = 0, b = nbin - 1;
+    for (; b > 0; b--) {
+      const int c = bin_cnt_prev[b];
+      if (env < off + c) break;
+      off += c;
+    }
+    order[env] = bin_items_prev[(size_t)b * n + min(env - off, n - 1)];
+    for (int k = env; k < nbin; k += n) bin_cnt_next[k] = 0; // (n may be smaller than the number of bins)
+  }
   if (done) done[env] = 0;
   float q[7], qd[7];
 #pragma unroll
   for (int j = 0; j < 7; j++) { q[j] = qpos[(size_t)env * QPAD + j]; qd[j] = qvel[(size_t)env * QPAD + j]; }
-  arm_forward(env, 0, policy_step != 0, q, qd, act, task, armbuf);
+  arm_forward(0, policy_step != 0, q, qd, act + (size_t)env * dm.adim, task + (size_t)env * USIM_TASK_DIM, armbuf + (size_t)env * ARMBUF);
 }
 
 // ---------------------------------------------------------------- reset (ultrasound.py:416-477, :749-887)
-// One thread per env: Philox draws keyed by (seed, global env id, episode), trajectory, DLS inverse
-// kinematics for the initial joint pose, state initialisation, then the arm part of the post-reset forward pass
-// (sim.forward() with ctrl = 0, ultrasound.py:431); the solve kernel (mode 1) that fills the contact-force statistics and the
-// observation runs afterwards.  With `tobs` the observation of the terminal step is kept first (SB3 `terminal_observation`).
-__global__ void __launch_bounds__(64) reset_kernel(int n, const uint8_t* __restrict__ mask, float* __restrict__ qpos, float* __restrict__ qvel,
+// One thread per env: Philox draws keyed by (seed, global env id, episode number), trajectory, DLS inverse kinematics for the
+// initial joint pose, state initialisation, then the arm part of the post-reset forward pass (sim.forward() with ctrl = 0,
+// ultrasound.py:431); the solve kernel (mode 1) that fills the contact-force statistics and the observation runs afterwards.
+// The result depends on nothing but (seed, env id, episode number), so it can be made ahead of time:
+//   live mode (items == nullptr): usim_reset -- the envs selected by `mask`, episode number from the live record, rows written to
+//     the live state; files a request to prepare episode number + 2 into the slot this episode number belongs to.
+//   prepare mode: works through the (env, episode number) requests of `items`; rows go to slot (episode number & 1) of the env
+//     (qpos / task: [2][n][...]), the arm record to row `item` of `armbuf`.  A reset state is at rest: no qvel / warm rows.
+__global__ void __launch_bounds__(32) reset_kernel(int n, const uint8_t* __restrict__ mask, float* __restrict__ qpos, float* __restrict__ qvel,
                                                    float* __restrict__ warm, float* __restrict__ task, float* __restrict__ armbuf,
-                                                   const float* __restrict__ obs, float* __restrict__ tobs) {
-  int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= n) return;
-  if (mask && !mask[env]) return;
-  if (obs && tobs) {
-    for (int i = 0; i < USIM_OBS_DIM; i++) tobs[(size_t)env * USIM_OBS_DIM + i] = obs[(size_t)env * USIM_OBS_DIM + i];
+                                                   const int* __restrict__ items, const int* __restrict__ nitems,
+                                                   int* __restrict__ req_list, int* __restrict__ req_cnt) {
+  const int total = items ? *nitems : n;
+#pragma unroll 1
+  for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
+  int env = item;
+  size_t row = item;
+  unsigned ep;
+  if (items) {
+    env = items[2 * item];
+    ep = (unsigned)items[2 * item + 1];
+    row = (size_t)(ep & 1u) * n + env;
+  } else {
+    if (mask && !mask[env]) continue;
+    ep = (unsigned)task[(size_t)env * USIM_TASK_DIM + USIM_TS_EPISODE];
+    if (req_list) {
+      const int p = atomicAdd(req_cnt, 1);
+      req_list[2 * p] = env; req_list[2 * p + 1] = (int)ep + 2;
+    }
   }
-  float* ts = task + (size_t)env * USIM_TASK_DIM;
-  unsigned ep = (unsigned)ts[USIM_TS_EPISODE], gid = (unsigned)(dm.env_off + env), r[4];
+  float* ts = task + row * USIM_TASK_DIM;
+  float* ab = armbuf + (size_t)item * ARMBUF;
+  unsigned gid = (unsigned)(dm.env_off + env), r[4];
   float kst = -dm.solref_smooth[0], bst = -dm.solref_smooth[1];
   if (dm.solref_rand) { // ultrasound.py:291-297
     philox(dm.seed_lo, dm.seed_hi, gid, ep, 0, 0, r);
@@ -353,10 +393,13 @@ __global__ void __launch_bounds__(64) reset_kernel(int n, const uint8_t* __restr
   for (int i = 0; i < USIM_TASK_DIM; i++) ts[i] = 0.f;
   ts[USIM_TS_EPISODE] = (float)(ep + 1);
   ts[USIM_TS_STIFFNESS] = kst; ts[USIM_TS_DAMPING] = bst;
-  float* qp = qpos + (size_t)env * QPAD;
-  float* qv = qvel + (size_t)env * QPAD;
-  float* wm = warm + (size_t)env * QPAD;
-  for (int i = 0; i < QPAD; i++) { qp[i] = 0.f; qv[i] = 0.f; wm[i] = 0.f; }
+  float* qp = qpos + row * QPAD;
+  for (int i = 0; i < QPAD; i++) qp[i] = 0.f;
+  if (qvel) {
+    float* qv = qvel + row * QPAD;
+    float* wm = warm + row * QPAD;
+    for (int i = 0; i < QPAD; i++) { qv[i] = 0.f; wm[i] = 0.f; }
+  }
   float tx = 0.f, ty = 0.f, tz = 0.8f + 0.005f + 0.0522f;
   if (dm.soft) {
     for (int i = 0; i < 7; i++) qp[7 + i] = dm.torso_qpos0[i];
@@ -401,12 +444,16 @@ __global__ void __launch_bounds__(64) reset_kernel(int n, const uint8_t* __restr
     target = target + ld3(dm.eef_bias);
     float G[9];
     goal_mat(G);
+    float en_prev = 1e30f;
+#pragma unroll 1
     for (int it = 0; it < 60; it++) {
       arm_fk(q, k);
       v3 ep3 = target - k.site, eo = ori_error(G, k.Rs);
       float err[6] = {ep3.x, ep3.y, ep3.z, eo.x, eo.y, eo.z};
       float en = sqrtf(dot(ep3, ep3) + dot(eo, eo));
-      if (en < 2e-6f) break;
+      // converged, or stalled on the fp32 floor of the forward kinematics (~1e-6: the residual no longer halves)
+      if (en < 2e-6f || (en < 1e-4f && en > 0.5f * en_prev)) break;
+      en_prev = en;
       float J[42], A[36];
       arm_jac(k, k.site, J);
 #pragma unroll
@@ -441,5 +488,15 @@ __global__ void __launch_bounds__(64) reset_kernel(int n, const uint8_t* __restr
 #pragma unroll
   for (int i = 0; i < 9; i++) ts[USIM_TS_GOAL_ORI + i] = k.Rs[i];
   const float qd0[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  arm_forward(env, 1, false, q, qd0, nullptr, task, armbuf);
+  arm_forward(1, false, q, qd0, nullptr, ts, ab);
+  } // work items
+}
+
+// first reset of a handle: request the two episodes that follow the first one (numbers 1 and 2) for EVERY env
+__global__ void fill_requests_kernel(int n, int* __restrict__ req_list, int* __restrict__ req_cnt) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  const int p = atomicAdd(req_cnt, 2);
+  req_list[2 * p] = env; req_list[2 * p + 1] = 1;
+  req_list[2 * p + 2] = env; req_list[2 * p + 3] = 2;
 }

@@ -9,7 +9,7 @@
 #define DEV_MAXC USIM_MAX_CONTACTS
 #define NPART_MAX 272
 #define QPAD 288   // row pitch (floats) of qpos / qvel / warm in HBM: 284 -> 288 = 9 x 128 B
-#define ARMBUF 176 // row pitch of the arm intermediate record
+#define ARMBUF 180 // row pitch of the arm intermediate record (a multiple of 4 floats: rows are moved by 16-byte bulk copies)
 
 // arm-record layout (floats), written by the arm kernel, read by the solve kernel
 enum {
@@ -24,7 +24,8 @@ enum {
   AB_PBACK = 141,  // 3
   AB_TAU0 = 144,   // 3 F/T torque: velocity-product + gravity part about the site (world)
   AB_JFT = 147,    // 21 F/T torque: linear map from arm qacc (world)
-  AB_QUAT = 168    // 4 eef quaternion xyzw, w >= 0
+  AB_QUAT = 168,   // 4 eef quaternion xyzw, w >= 0
+  AB_DX = 172      // 7 warm-start shift of the arm: M^-1 (qfrc_smooth - previous qfrc_smooth)
 };
 
 struct DevModel {

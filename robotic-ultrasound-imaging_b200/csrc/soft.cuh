@@ -43,6 +43,13 @@
 #ifndef CHEB_C
 #define CHEB_C 1.6f
 #endif
+// Arm part of the warm start: the previous qacc shifted by M^-1 (qfrc_smooth_now - qfrc_smooth_previous), computed by the arm kernel
+// with the Cholesky factor it holds anyway.  A fresh action every step moves qfrc_smooth of the arm by the change of the controller
+// torque; without the shift the previous qacc is a poor start for the 7 arm unknowns (6.4 CG iterations with random actions, 4.0 with
+// a constant one).
+#ifndef ARM_SHIFT
+#define ARM_SHIFT 1
+#endif
 #ifndef NORESTART
 #define NORESTART 1 // 1: keep the Polak-Ribiere direction across a preconditioner rebuild (flexible CG: beta uses the previous pg, made with the previous preconditioner) instead of restarting; measured 0.464 ms vs 0.485 ms
 #endif
@@ -91,6 +98,7 @@ struct __align__(16) WS {
   float lsign[7], lD[7], laref[7];
   float Dt, areft;
   int ncon, okf;
+  int consume;                                         // this env's episode ended and a prepared reset slot takes over (K9 -> all threads)
   int cnt[2][WPE];                                     // cross-warp prefix of the contact compaction (double buffered)
 };
 static_assert(sizeof(WS) + 1024 <= 233472 / MINB, "WS must leave room for MINB CTAs per SM");
@@ -276,50 +284,112 @@ __device__ __forceinline__ void chol7_solve(const float* L, float* x) {
   }
 }
 
-// mode: 0 = env step (last physics substep of a control step: integrates, then the task epilogue), 1 = reset forward (no
-// integration; initialises the running statistics), 2 = intermediate physics substep (integrates, no task epilogue / outputs)
-__global__ void __launch_bounds__(NT, MINB) solve_kernel(
-    int n, int mode, const uint8_t* __restrict__ mask, float* __restrict__ qpos, float* __restrict__ qvel, float* __restrict__ warm,
-    float* __restrict__ task, const float* __restrict__ armbuf, PartTables pt, const int2* __restrict__ eq_pairs,
-    float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
-    float* __restrict__ diag, int* __restrict__ ncon_out, int* __restrict__ geom1_out, int* __restrict__ geom2_out,
-    float* __restrict__ dist_out, int* __restrict__ counters /* [0] diverged env steps, [1] env steps whose contact list overflowed */) {
+// Launch slots are ordered longest-solve-first: every launch files its envs into NBIN bins by the number of CG iterations they
+// took; the arm kernel of the next physics step flattens the bins (highest first) into `order`, and CTA j of the next solve launch
+// takes env order[j].  The block scheduler hands CTAs out in index order, so the slow envs start first and the tail of the launch
+// (3.5 waves at 4096 envs) is made of the quick ones.  Which CTA runs an env never changes its result.
+#define NBIN 16
+#define SLOT_OBS 20 // row pitch of a prepared observation (19 used)
+
+// Reset pipeline.  The state an env is reset to is a pure function of (seed, global env id, episode number): it is PREPARED ahead of
+// time, off the critical path, into one of two per-env slots (slot k holds an episode number with parity k), by the reset kernel +
+// this kernel in forward-only mode on a side stream.  When an episode ends inside a step (auto-reset, SB3 VecEnv semantics) the CTA
+// that stepped the env copies the prepared rows over the live state -- no extra launch -- and files a request to prepare the
+// episode after next into the slot it has just emptied.
+struct SolveArgs {
+  int n;          // envs of this handle
+  int mode;       // 0 = env step (last physics substep of a control step: integrates, then the task epilogue), 1 = reset forward (no
+                  // integration; initialises the running statistics), 2 = intermediate physics substep (integrates, no task epilogue)
+  int prep;       // 1: prepare mode (mode must be 1): work items and state rows come from the request list / the slots
+  int auto_reset; // mode 0: an env whose episode ends takes over its prepared slot
+  const uint8_t* mask; // mode 1, live: envs to process (nullptr: all)
+  float *qpos, *qvel, *warm, *task;
+  const float* armbuf; // live: [n][ARMBUF]; prepare mode: [items][ARMBUF]
+  PartTables pt;
+  const int2* eq_pairs;
+  float *obs, *rew;
+  uint8_t* done;
+  float* tobs;
+  float* diag;
+  int *ncon_out, *geom1_out, *geom2_out;
+  float* dist_out;
+  int* counters;  // [0] diverged env steps, [1] env steps whose contact list overflowed
+  const int* order;          // env of launch slot j (nullptr: identity)
+  int *bin_cnt, *bin_items;  // [NBIN], [NBIN][n]: where this launch files its envs (nullptr: not filed)
+  float *slot_qpos, *slot_task, *slot_obs; // [2][n][QPAD | USIM_TASK_DIM | SLOT_OBS]
+  int *req_list, *req_cnt;         // (env, episode number) pairs to prepare, appended by this launch
+  const int *prep_items, *prep_n;  // prepare mode: the requests this launch works through
+};
+
+__global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  const int env = blockIdx.x;
-  if (env >= n) return;
-  if (mask && !mask[env]) return;
+  const int n = a.n, mode = a.mode;
+  const PartTables pt = a.pt;
+  const int2* __restrict__ eq_pairs = a.eq_pairs;
   WS& w = *reinterpret_cast<WS*>(smem_raw);
-  float* ts_g = task + (size_t)env * USIM_TASK_DIM;
-  if (mode != 1 && ts_g[USIM_TS_DONE] != 0.f) return;
-  const int np = dm.soft ? dm.npart : 0;
-  const int nv = 7 + (dm.soft ? 6 + np : 0);
-  const float h = dm.h;
-  float* qp_g = qpos + (size_t)env * QPAD;
-  float* qv_g = qvel + (size_t)env * QPAD;
-  float* wm_g = warm + (size_t)env * QPAD;
-
-  // ------------------------------------------------------------------ load: five TMA bulk copies, one mbarrier
   static_assert(offsetof(WS, qrow) % 16 == 0 && offsetof(WS, x) % 16 == 0 && offsetof(WS, hs) % 16 == 0 && offsetof(WS, ab) % 16 == 0 &&
                     offsetof(WS, ts) % 16 == 0 && (QPAD * 4) % 16 == 0 && (ARMBUF * 4) % 16 == 0 && (USIM_TASK_DIM * 4) % 16 == 0,
                 "TMA bulk copies need 16-byte aligned rows");
   if (tid == 0) mbar_init(&w.bar, 1);
   env_sync();
+  unsigned phase = 0;
+  const int nitems = a.prep ? *a.prep_n : n;
+  // one trip per CTA for the env step (grid = n); the prepare launch walks its request list with a small fixed grid
+#pragma unroll 1
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+  int env = item;
+  float *qp_g, *qv_g, *wm_g, *ts_g, *obs_row;
+  const float* ab_g;
+  if (a.prep) {
+    env = a.prep_items[2 * item];
+    const size_t row = (size_t)(a.prep_items[2 * item + 1] & 1) * n + env;
+    qp_g = a.slot_qpos + row * QPAD; qv_g = nullptr; wm_g = nullptr; // a reset state is at rest: velocity and warm start are zero
+    ts_g = a.slot_task + row * USIM_TASK_DIM;
+    ab_g = a.armbuf + (size_t)item * ARMBUF;
+    obs_row = a.slot_obs + row * SLOT_OBS;
+  } else {
+    if (a.order) env = a.order[item];
+    if (a.mask && !a.mask[env]) continue;
+    qp_g = a.qpos + (size_t)env * QPAD; qv_g = a.qvel + (size_t)env * QPAD; wm_g = a.warm + (size_t)env * QPAD;
+    ts_g = a.task + (size_t)env * USIM_TASK_DIM;
+    ab_g = a.armbuf + (size_t)env * ARMBUF;
+    obs_row = a.obs ? a.obs + (size_t)env * USIM_OBS_DIM : nullptr;
+  }
+  if (mode != 1 && ts_g[USIM_TS_DONE] != 0.f) { // terminated env: frozen until reset; it keeps its place in the launch order
+    if (tid == 0 && a.bin_cnt) a.bin_items[atomicAdd(a.bin_cnt, 1)] = env;
+    continue;
+  }
+  const int np = dm.soft ? dm.npart : 0;
+  const int nv = 7 + (dm.soft ? 6 + np : 0);
+  const float h = dm.h;
+
+  // ------------------------------------------------------------------ load: five TMA bulk copies, one mbarrier
   if (tid == 0) {
-    mbar_expect_tx(&w.bar, (3 * QPAD + ARMBUF + USIM_TASK_DIM) * 4);
+    mbar_expect_tx(&w.bar, ((qv_g ? 3 : 1) * QPAD + ARMBUF + USIM_TASK_DIM) * 4);
     tma_load_row(w.qrow, qp_g, QPAD * 4, &w.bar);
-    tma_load_row(w.x, wm_g, QPAD * 4, &w.bar);
-    tma_load_row(w.hs, qv_g, QPAD * 4, &w.bar);
-    tma_load_row(w.ab, armbuf + (size_t)env * ARMBUF, ARMBUF * 4, &w.bar);
+    if (qv_g) {
+      tma_load_row(w.x, wm_g, QPAD * 4, &w.bar);
+      tma_load_row(w.hs, qv_g, QPAD * 4, &w.bar);
+    }
+    tma_load_row(w.ab, ab_g, ARMBUF * 4, &w.bar);
     tma_load_row(w.ts, ts_g, USIM_TASK_DIM * 4, &w.bar);
   }
   // (overlapped with the copies)
   for (int i = tid; i < QPAD; i += NT) { w.grad[i] = 0.f; w.pg[i] = 0.f; w.s[i] = 0.f; }
+  if (!qv_g)
+    for (int i = tid; i < QPAD; i += NT) { w.x[i] = 0.f; w.hs[i] = 0.f; }
   for (int i = tid; i < np; i += NT) { w.cslot[i] = -1; w.cslot2[i] = -1; }
   for (int i = tid; i < 49; i += NT) w.Sf[i] = (i % 8 == 0) ? 1.f : 0.f; // identity: row/col 6 of the padded 6x6 stay like this
-  mbar_wait(&w.bar, 0);
+  mbar_wait(&w.bar, phase);
+  phase ^= 1;
   for (int i = nv + tid; i < QPAD; i += NT) w.x[i] = 0.f; // the solver vectors are zero beyond nv
-  if (tid < 7) w.qdarm[tid] = w.hs[tid];
+  if (tid < 7) {
+    w.qdarm[tid] = w.hs[tid];
+#if ARM_SHIFT
+    if (mode != 1) w.x[tid] += w.ab[AB_DX + tid]; // warm start of the arm follows the change of its applied force (arm kernel)
+#endif
+  }
   float quat[4] = {1, 0, 0, 0};
   if (dm.soft) {
     if (tid < 6) w.vf[tid] = w.hs[7 + tid];
@@ -546,7 +616,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
   const int ncon_found = ncon;
   if (ncon > DEV_MAXC) { // contacts beyond the cap are dropped: counted, never silent (usim_contact_overflow_count)
     ncon = DEV_MAXC;
-    if (tid == 0 && counters) atomicAdd(counters + 1, 1);
+    if (tid == 0 && a.counters) atomicAdd(a.counters + 1, 1);
   }
   env_sync();
 
@@ -581,7 +651,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     v3 ar = (-B) * rel - (K * imp * w.cfs[c]) * nn;
     w.cjv[0][c] = ar.x; w.cjv[1][c] = ar.y; w.cjv[2][c] = ar.z;
     w.czone[c] = 255; // "unknown": the first gradient evaluation always reports a change
-    if (dist_out) dist_out[(size_t)env * DEV_MAXC + c] = w.cfs[c]; // the depth leaves here: cfs becomes scratch
+    if (a.dist_out) a.dist_out[(size_t)env * DEV_MAXC + c] = w.cfs[c]; // the depth leaves here: cfs becomes scratch
   }
   env_sync();
 
@@ -1150,24 +1220,18 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     } else if (tid >= 7 && tid < 13) {
       w.hs[tid] = 0.f;
     }
-    fence_async_smem();
-    env_sync();
-    if (tid == 0) {
-      tma_store_row(qp_g, w.qrow, QPAD * 4);
-      tma_store_row(qv_g, w.hs, QPAD * 4);
-      tma_store_row(wm_g, w.x, QPAD * 4);
-    }
+    // (the new rows stay in shared memory until the task epilogue has decided whether the episode goes on)
   }
   env_sync();
 
   // ------------------------------------------------------------------ contact list / diagnostics
-  if (ncon_out) {
-    if (tid == 0) ncon_out[env] = ncon;
+  if (a.ncon_out) {
+    if (tid == 0) a.ncon_out[env] = ncon;
     for (int c = tid; c < ncon; c += NT) {
       int type = w.ctype[c], g1, g2;
       if (type == 2) { g1 = 1; g2 = 2; } else { g1 = 4 + w.cpart[c]; g2 = type == 0 ? 1 : 2; }
-      geom1_out[(size_t)env * DEV_MAXC + c] = g1;
-      geom2_out[(size_t)env * DEV_MAXC + c] = g2;
+      a.geom1_out[(size_t)env * DEV_MAXC + c] = g1;
+      a.geom2_out[(size_t)env * DEV_MAXC + c] = g2;
     }
   }
 
@@ -1181,6 +1245,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     xnorm2 = rd(w.rq, 0);
   }
   // ------------------------------------------------------------------ K9: task epilogue (lane 0)
+  if (tid == 0) w.consume = 0;
   if (tid == 0 && mode != 2) {
     float* ts = w.ts;
     v3 hv = mk(0, 0, 0);
@@ -1211,7 +1276,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
     if (bad) { // keep the outputs finite; the episode ends below and the reset wipes the state
       cfrc = mk(0, 0, 0); ft = mk(0, 0, 0); hv = mk(0, 0, 0);
       if (!isfinite(eef.x + eef.y + eef.z)) eef = ld3(ts + USIM_TS_TRAJ_PT);
-      if (counters) atomicAdd(counters, 1);
+      if (a.counters) atomicAdd(a.counters, 1);
     }
     if (mode == 0) {
       ts[USIM_TS_TIMESTEP] += 1.f;
@@ -1250,8 +1315,11 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
       o_fz = ts[USIM_TS_FZ_MEAN] - 5.f; o_dfz = 0.f; o_vel = ts[USIM_TS_VEL_MEAN] - 0.04f;
     }
     ts[USIM_TS_IN_CONTACT] = in_contact ? 1.f : 0.f;
-    if (obs) { // ultrasound.py:363-401
-      float* o = obs + (size_t)env * USIM_OBS_DIM;
+    // auto-reset (SB3 VecEnv semantics): the env takes over its prepared slot below; this step's observation is the terminal one
+    const bool consume = mode == 0 && a.auto_reset && dn;
+    w.consume = consume;
+    float* o = consume ? (a.tobs ? a.tobs + (size_t)env * USIM_OBS_DIM : nullptr) : obs_row;
+    if (o) { // ultrasound.py:363-401
       o[0] = cfrc.x; o[1] = cfrc.y; o[2] = cfrc.z; o[3] = ft.x; o[4] = ft.y; o[5] = ft.z; o[6] = hv.x; o[7] = hv.y; o[8] = hv.z;
       o[9] = o_fz; o[10] = o_dfz; o[11] = o_vel;
       o[12] = eef.x - o_tp.x; o[13] = eef.y - o_tp.y; o[14] = eef.z - o_tp.z;
@@ -1259,11 +1327,11 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
       difference_quat(quat_e, gq, o + 15); // xyzw arrays through a wxyz routine (:390)
     }
     if (mode == 0) {
-      if (rew) rew[env] = reward;
-      if (done) done[env] = (uint8_t)dn;
+      if (a.rew) a.rew[env] = reward;
+      if (a.done) a.done[env] = (uint8_t)dn;
     }
-    if (diag) {
-      float* d = diag + (size_t)env * USIM_DIAG_DIM;
+    if (a.diag) {
+      float* d = a.diag + (size_t)env * USIM_DIAG_DIM;
       d[0] = cfrc.x; d[1] = cfrc.y; d[2] = cfrc.z; d[3] = ft.x; d[4] = ft.y; d[5] = ft.z; d[6] = eef.x; d[7] = eef.y; d[8] = eef.z;
       d[9] = quat_e[0]; d[10] = quat_e[1]; d[11] = quat_e[2]; d[12] = quat_e[3];
 #pragma unroll
@@ -1274,12 +1342,45 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(
       d[23] = (float)(3 * ncon + nlim + (dm.soft ? 2 * 0 + np + dm.npair + 1 : 0));
     }
   }
-  env_sync();
-  // task record back to HBM, then wait until the bulk stores have finished READING shared memory (the CTA may not exit before)
-  fence_async_smem();
-  env_sync();
-  if (tid == 0) {
-    tma_store_row(ts_g, w.ts, USIM_TASK_DIM * 4);
-    tma_store_commit_wait();
+  // file the env for the next launch's order: by the iterations it took; a freshly reset env (cold start) goes first
+  if (tid == 0 && a.bin_cnt) {
+    const int b = w.consume ? NBIN - 1 : min(iters, NBIN - 1);
+    a.bin_items[(size_t)b * n + atomicAdd(a.bin_cnt + b, 1)] = env;
   }
+  env_sync();
+  if (w.consume) {
+    // The episode is over and auto-reset is on: the prepared slot (episode number E = the live record's counter, slot E & 1) becomes
+    // the live state.  Velocity and warm start of a reset state are zero.  Then ask for episode E + 2 to be prepared in this slot.
+    const int E = (int)w.ts[USIM_TS_EPISODE];
+    const size_t row = (size_t)(E & 1) * n + env;
+    const float4* sq = reinterpret_cast<const float4*>(a.slot_qpos + row * QPAD);
+    const float4* st = reinterpret_cast<const float4*>(a.slot_task + row * USIM_TASK_DIM);
+    float4 *dq = reinterpret_cast<float4*>(qp_g), *dvv = reinterpret_cast<float4*>(qv_g), *dw = reinterpret_cast<float4*>(wm_g);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < QPAD / 4; i += NT) { dq[i] = sq[i]; dvv[i] = z4; dw[i] = z4; }
+    for (int i = tid; i < USIM_TASK_DIM / 4; i += NT) reinterpret_cast<float4*>(ts_g)[i] = st[i];
+    if (obs_row && tid < USIM_OBS_DIM) obs_row[tid] = a.slot_obs[row * SLOT_OBS + tid];
+    env_sync(); // every thread has read the slot: it may be overwritten from here on
+    if (tid == 0) {
+      __threadfence();
+      const int p = atomicAdd(a.req_cnt, 1);
+      a.req_list[2 * p] = env; a.req_list[2 * p + 1] = E + 2;
+    }
+  } else {
+    // state rows and task record back to HBM (TMA bulk stores out of the shared-memory image), then wait until the stores have
+    // finished READING shared memory: the next trip / the exit of the CTA may not come before
+    fence_async_smem();
+    env_sync();
+    if (tid == 0) {
+      if (mode != 1) {
+        tma_store_row(qp_g, w.qrow, QPAD * 4);
+        tma_store_row(qv_g, w.hs, QPAD * 4);
+        tma_store_row(wm_g, w.x, QPAD * 4);
+      }
+      tma_store_row(ts_g, w.ts, USIM_TASK_DIM * 4);
+      tma_store_commit_wait();
+    }
+  }
+  env_sync();
+  } // work items
 }

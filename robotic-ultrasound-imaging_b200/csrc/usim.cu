@@ -12,6 +12,9 @@
 #include "common.cuh"
 #include "soft.cuh"
 
+#ifndef PREP_GRID
+#define PREP_GRID 296 // CTAs of the forward-only solve launch that prepares reset states (walks the request list)
+#endif
 #ifndef ARM_BLOCK
 #define ARM_BLOCK 32 // threads per CTA of the thread-per-env arm kernel (latency bound: 128 one-warp CTAs on 128 SMs; measured 21.7 us vs 25.0 us for 64)
 #endif
@@ -45,6 +48,17 @@ struct usim_handle {
   float *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr, *d_tobs = nullptr;
   uint8_t* d_done = nullptr;
   uint8_t* d_resetmask = nullptr;
+  // launch order of the solve kernel (longest solve first): bins filled by launch T, flattened by the arm kernel of launch T + 1
+  int *bin_cnt = nullptr, *bin_items = nullptr, *order = nullptr; // [2][NBIN], [2][NBIN][n], [n]
+  int64_t solve_tick = 0;
+  // reset pipeline: two prepared reset states per env (slot k holds an episode number of parity k), made on a side stream
+  float *slot_qpos = nullptr, *slot_task = nullptr, *slot_obs = nullptr, *prep_armbuf = nullptr;
+  int *req_list = nullptr, *req_cnt = nullptr; // [2][2 * 3n], [2]: request lists, double buffered by producer tick
+  int64_t prod_tick = 0;
+  bool slots_init = false;
+  cudaStream_t prep_stream = nullptr;
+  cudaEvent_t ev_prod = nullptr, ev_prep[2] = {nullptr, nullptr};
+  bool ev_prep_valid[2] = {false, false};
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_state = nullptr; // recorded on the caller's stream after every state-mutating call: usim_step_host waits on it
   bool ev_state_valid = false, timing = false;
@@ -233,6 +247,35 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   CKH(cudaMemset(h->d_tobs, 0, N * USIM_OBS_DIM * sizeof(float)));
   CKH(cudaEventCreateWithFlags(&h->ev_state, cudaEventDisableTiming));
   CKH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  {
+    // launch-order bins: before the first launch every env sits in bin 0 of buffer 1 (identity order)
+    CKH(cudaMalloc((void**)&h->bin_cnt, 2 * NBIN * sizeof(int)));
+    CKH(cudaMalloc((void**)&h->bin_items, 2 * (size_t)NBIN * N * sizeof(int)));
+    CKH(cudaMalloc((void**)&h->order, N * sizeof(int)));
+    std::vector<int> cnt(2 * NBIN, 0), ident(N);
+    cnt[NBIN] = (int)N;
+    for (size_t e = 0; e < N; e++) ident[e] = (int)e;
+    CKH(cudaMemcpy(h->bin_cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CKH(cudaMemcpy(h->bin_items + (size_t)NBIN * N, ident.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    CKH(cudaMemcpy(h->order, ident.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    // reset slots + request lists (at most n requests per producer launch, 2n at the first reset)
+    CKH(cudaMalloc((void**)&h->slot_qpos, 2 * N * QPAD * sizeof(float)));
+    CKH(cudaMalloc((void**)&h->slot_task, 2 * N * USIM_TASK_DIM * sizeof(float)));
+    CKH(cudaMalloc((void**)&h->slot_obs, 2 * N * SLOT_OBS * sizeof(float)));
+    CKH(cudaMalloc((void**)&h->prep_armbuf, 3 * N * ARMBUF * sizeof(float)));
+    CKH(cudaMalloc((void**)&h->req_list, 2 * 2 * 3 * N * sizeof(int)));
+    CKH(cudaMalloc((void**)&h->req_cnt, 2 * sizeof(int)));
+    CKH(cudaMemset(h->slot_qpos, 0, 2 * N * QPAD * sizeof(float)));
+    CKH(cudaMemset(h->slot_task, 0, 2 * N * USIM_TASK_DIM * sizeof(float)));
+    CKH(cudaMemset(h->slot_obs, 0, 2 * N * SLOT_OBS * sizeof(float)));
+    CKH(cudaMemset(h->req_cnt, 0, 2 * sizeof(int)));
+    int lo = 0, hi = 0;
+    CKH(cudaDeviceGetStreamPriorityRange(&lo, &hi)); // (hi = numerically lowest = greatest priority)
+    CKH(cudaStreamCreateWithPriority(&h->prep_stream, cudaStreamNonBlocking, hi));
+    CKH(cudaEventCreateWithFlags(&h->ev_prod, cudaEventDisableTiming));
+    CKH(cudaEventCreateWithFlags(&h->ev_prep[0], cudaEventDisableTiming));
+    CKH(cudaEventCreateWithFlags(&h->ev_prep[1], cudaEventDisableTiming));
+  }
   h->smem = sizeof(WS);
   if (const char* pad = getenv("USIM_SMEM_PAD")) h->smem += (size_t)atoi(pad); // developer knob: trade resident CTAs for L1 capacity
   CKH(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
@@ -249,12 +292,15 @@ int usim_destroy(usim_handle* h) {
   for (auto& p : h->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   void* dev[] = {h->counters, h->qpos, h->qvel, h->warm, h->task, h->armbuf, h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->ax4,
                  h->ps4, h->nb4, h->eq_pairs, h->d_act, h->d_obs, h->d_tobs, h->d_rew,
-                 h->d_done, h->d_resetmask};
+                 h->d_done, h->d_resetmask, h->bin_cnt, h->bin_items, h->order, h->slot_qpos, h->slot_task, h->slot_obs, h->prep_armbuf,
+                 h->req_list, h->req_cnt};
   for (void* p : dev) if (p) cudaFree(p);
   void* host[] = {h->h_act, h->h_obs, h->h_tobs, h->h_rew, h->h_done};
   for (void* p : host) if (p) cudaFreeHost(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->ev_state) cudaEventDestroy(h->ev_state);
+  if (h->prep_stream) cudaStreamDestroy(h->prep_stream);
+  for (cudaEvent_t e : {h->ev_prod, h->ev_prep[0], h->ev_prep[1]}) if (e) cudaEventDestroy(e);
   delete h;
   return 0;
 }
@@ -281,33 +327,81 @@ static int mark_state(usim_handle* h, cudaStream_t s) {
   return 0;
 }
 
-// forward pass: mode 0 = env step (arm kernel + solve kernel; with more than one physics substep per control step the pair is
-// repeated, the OSC goal is set on the first and the task epilogue runs after the last: robosuite MujocoEnv.step), mode 1 = post-reset
-// forward (solve kernel only: the reset kernel has already run the arm part)
-static int launch_forward(usim_handle* h, int mode, const uint8_t* mask, const float* act, float* obs, float* rew, uint8_t* done,
-                          cudaStream_t s) {
-  const int n = h->n, nsub = mode == 0 ? h->substeps : 1;
+static SolveArgs base_args(usim_handle* h, int mode) {
+  SolveArgs a;
+  memset(&a, 0, sizeof a);
+  a.n = h->n; a.mode = mode;
+  a.qpos = h->qpos; a.qvel = h->qvel; a.warm = h->warm; a.task = h->task; a.armbuf = h->armbuf;
+  a.pt = tables(h); a.eq_pairs = h->eq_pairs;
+  a.diag = h->diag; a.ncon_out = h->ncon; a.geom1_out = h->geom1; a.geom2_out = h->geom2; a.dist_out = h->cdist;
+  a.counters = h->counters;
+  a.slot_qpos = h->slot_qpos; a.slot_task = h->slot_task; a.slot_obs = h->slot_obs;
+  return a;
+}
+
+// Producer launches (the last solve launch of an auto-reset step, an explicit reset) append prepare requests to list (tick & 1).
+// Before one starts, the prepare run that last worked through that list (two producers ago) must have finished -- it always has,
+// in practice: it had a whole step to do so.  This also orders every slot write before the step that may read it.
+static int producer_begin(usim_handle* h, cudaStream_t s) {
+  const int b = (int)(h->prod_tick & 1);
+  if (h->ev_prep_valid[b]) CK(cudaStreamWaitEvent(s, h->ev_prep[b], 0));
+  return 0;
+}
+// After the producer: work through its request list on the side stream (reset kernel in prepare mode, forward-only solve on the
+// slots), concurrently with whatever the caller's stream does next.
+static int producer_end(usim_handle* h, cudaStream_t s) {
+  const int b = (int)(h->prod_tick & 1), n = h->n;
+  int* list = h->req_list + (size_t)b * 2 * 3 * n;
+  int* cnt = h->req_cnt + b;
+  CK(cudaEventRecord(h->ev_prod, s));
+  CK(cudaStreamWaitEvent(h->prep_stream, h->ev_prod, 0));
+  reset_kernel<<<64, 32, 0, h->prep_stream>>>(n, nullptr, h->slot_qpos, nullptr, nullptr, h->slot_task, h->prep_armbuf, list, cnt, nullptr, nullptr);
+  SolveArgs a = base_args(h, 1);
+  a.prep = 1; a.armbuf = h->prep_armbuf; a.prep_items = list; a.prep_n = cnt;
+  a.diag = nullptr; a.ncon_out = nullptr; a.geom1_out = nullptr; a.geom2_out = nullptr; a.dist_out = nullptr;
+  solve_kernel<<<PREP_GRID, NT, h->smem, h->prep_stream>>>(a);
+  CK(cudaMemsetAsync(cnt, 0, sizeof(int), h->prep_stream));
+  CK(cudaEventRecord(h->ev_prep[b], h->prep_stream));
+  h->ev_prep_valid[b] = true;
+  h->launches += 2;
+  h->prod_tick += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// One control step: int(control_timestep / timestep) physics substeps of (arm kernel, solve kernel); the OSC goal is set on the
+// first substep, the task epilogue -- and, with auto_reset, the hand-over to a prepared reset state -- runs in the last solve launch
+// [robosuite MujocoEnv.step].
+static int launch_step(usim_handle* h, const float* act, float* obs, float* rew, uint8_t* done, float* tobs, int auto_reset, cudaStream_t s) {
+  const int n = h->n, nsub = h->substeps;
   for (int sub = 0; sub < nsub; sub++) {
     const bool last = sub == nsub - 1;
-    if (mode == 0) {
-      arm_kernel<<<(n + ARM_BLOCK - 1) / ARM_BLOCK, ARM_BLOCK, 0, s>>>(n, h->qpos, h->qvel, act, h->task, h->armbuf, sub == 0 ? done : nullptr,
-                                                                    sub == 0);
-      h->launches += 1;
+    const int b = (int)(h->solve_tick & 1); // this launch files into bins b; its order comes from bins 1 - b
+    arm_kernel<<<(n + ARM_BLOCK - 1) / ARM_BLOCK, ARM_BLOCK, 0, s>>>(
+        n, h->qpos, h->qvel, act, h->task, h->armbuf, sub == 0 ? done : nullptr, sub == 0, NBIN, h->bin_cnt + (1 - b) * NBIN,
+        h->bin_items + (size_t)(1 - b) * NBIN * n, h->bin_cnt + b * NBIN, h->order);
+    SolveArgs a = base_args(h, last ? 0 : 2);
+    a.obs = obs; a.rew = rew; a.done = done; a.tobs = tobs;
+    a.order = h->order; a.bin_cnt = h->bin_cnt + b * NBIN; a.bin_items = h->bin_items + (size_t)b * NBIN * n;
+    if (last && auto_reset) {
+      if (producer_begin(h, s)) return -1;
+      a.auto_reset = 1;
+      a.req_list = h->req_list + (size_t)(h->prod_tick & 1) * 2 * 3 * n; a.req_cnt = h->req_cnt + (h->prod_tick & 1);
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    bool timed = h->timing && mode == 0 && h->pending.size() < 4096; // bounded: the caller drains with usim_kernel_time
+    bool timed = h->timing && h->pending.size() < 4096; // bounded: the caller drains with usim_kernel_time
     if (timed) {
       CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
       CK(cudaEventRecord(e0, s));
     }
-    solve_kernel<<<n, NT, h->smem, s>>>(
-        n, mode == 0 && !last ? 2 : mode, mask, h->qpos, h->qvel, h->warm, h->task, h->armbuf, tables(h), h->eq_pairs, obs, rew, done,
-        h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->counters);
+    solve_kernel<<<n, NT, h->smem, s>>>(a);
     if (timed) {
       CK(cudaEventRecord(e1, s));
       h->pending.emplace_back(e0, e1);
     }
-    h->launches += 1;
+    h->launches += 2;
+    h->solve_tick += 1;
+    if (last && auto_reset && producer_end(h, s)) return -1;
   }
   CK(cudaGetLastError());
   return 0;
@@ -317,28 +411,36 @@ int usim_reset(usim_handle* h, const uint8_t* mask_dev, float* obs_dev, void* st
   if (!h) return fail("usim_reset: null handle");
   if (activate(h)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
-  reset_kernel<<<(h->n + 63) / 64, 64, 0, s>>>(h->n, mask_dev, h->qpos, h->qvel, h->warm, h->task, h->armbuf, nullptr, nullptr);
-  h->launches += 1;
+  const int n = h->n;
+  if (producer_begin(h, s)) return -1;
+  int* list = h->req_list + (size_t)(h->prod_tick & 1) * 2 * 3 * n;
+  int* cnt = h->req_cnt + (h->prod_tick & 1);
+  const bool first = !h->slots_init;
+  if (first) { // nothing prepared yet: the two episodes after the first one, for every env (all episode counters are 0 here)
+    fill_requests_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, list, cnt);
+    h->slots_init = true;
+    h->launches += 1;
+  }
+  // the reset itself, in place and in stream order: reset kernel (live mode) + forward-only solve on the live state
+  reset_kernel<<<(n + 31) / 32, 32, 0, s>>>(n, mask_dev, h->qpos, h->qvel, h->warm, h->task, h->armbuf, nullptr, nullptr,
+                                           first ? nullptr : list, first ? nullptr : cnt);
+  SolveArgs a = base_args(h, 1);
+  a.mask = mask_dev; a.obs = obs_dev;
+  solve_kernel<<<n, NT, h->smem, s>>>(a);
+  h->launches += 2;
   CK(cudaGetLastError());
-  if (launch_forward(h, 1, mask_dev, nullptr, obs_dev, nullptr, nullptr, s)) return -1;
+  if (producer_end(h, s)) return -1;
   return mark_state(h, s);
 }
 
-// One env step = 4 launches: arm_kernel (also clears `done`), solve_kernel, and for auto-reset reset_kernel (terminal observation,
-// reset, arm forward; masked by `done`) + solve_kernel in forward-only mode (masked by `done`).
 int usim_step(usim_handle* h, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, float* term_obs_dev,
               int auto_reset, void* stream) {
   if (!h) return fail("usim_step: null handle");
   if (!act_dev || !done_dev) return fail("usim_step: act_dev and done_dev are required");
   if (activate(h)) return -1;
   cudaStream_t s = (cudaStream_t)stream;
-  if (launch_forward(h, 0, nullptr, act_dev, obs_dev, rew_dev, done_dev, s)) return -1;
-  if (auto_reset) {
-    reset_kernel<<<(h->n + 63) / 64, 64, 0, s>>>(h->n, done_dev, h->qpos, h->qvel, h->warm, h->task, h->armbuf, obs_dev, term_obs_dev);
-    h->launches += 1;
-    if (launch_forward(h, 1, done_dev, nullptr, obs_dev, nullptr, nullptr, s)) return -1;
-  }
-  CK(cudaGetLastError());
+  if (auto_reset && !h->slots_init) return fail("usim_step: auto_reset needs a usim_reset first (no reset state has been prepared)");
+  if (launch_step(h, act_dev, obs_dev, rew_dev, done_dev, term_obs_dev, auto_reset, s)) return -1;
   return mark_state(h, s);
 }
 

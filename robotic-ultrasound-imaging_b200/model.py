@@ -196,6 +196,11 @@ class SceneParams:
     probe_radius: float = 0.05
     probe_tip_z: float = -0.05  # tip-sphere centre (tip surface at the grip_site origin)
     probe_back_z: float = -0.10
+    # general form of the substituted capsule (probe-body frame, metres): segment end points and centre of mass; None = the
+    # axial capsule above ((0,0,probe_tip_z) .. (0,0,probe_back_z), COM at the middle of the segment)
+    probe_seg_a: Tuple[float, float, float] | None = None
+    probe_seg_b: Tuple[float, float, float] | None = None
+    probe_com: Tuple[float, float, float] | None = None
 
     # ---- soft composite (in tree): soft_box.xml (type box) or soft_human_torso.xml (type cylinder, `use_box_torso=False`)
     comp_type: str = "box"
@@ -276,6 +281,16 @@ def _composite_box(p: SceneParams):
     return np.array(pos), names, np.array(pairs, dtype=np.int32)
 
 
+def probe_geometry(p: SceneParams):
+    """(segment end points [2,3], COM [3], inertia about the COM [3,3]) of the probe capsule in the probe-body frame."""
+    a = np.asarray(p.probe_seg_a if p.probe_seg_a is not None else (0.0, 0.0, p.probe_tip_z), float)
+    b = np.asarray(p.probe_seg_b if p.probe_seg_b is not None else (0.0, 0.0, p.probe_back_z), float)
+    com = np.asarray(p.probe_com, float) if p.probe_com is not None else 0.5 * (a + b)
+    hl = 0.5 * np.linalg.norm(b - a)
+    Rc = quat2mat(z2quat(b - a)) if hl > 1e-12 else np.eye(3)
+    return np.array([a, b]), com, Rc @ capsule_inertia(p.probe_mass, p.probe_radius, hl) @ Rc.T
+
+
 def cylinder_torso_params(**kw) -> SceneParams:
     """`use_box_torso=False`: soft_human_torso.xml:8-14 (composite cylinder, bottom site at -0.05) and ultrasound.py:184-186."""
     return SceneParams(comp_type="cylinder", top_torso_offset=0.041, traj_y_range=0.05, torso_pos=(0.0, 0.0, 0.8 + 0.005 + 0.05), **kw)
@@ -321,16 +336,8 @@ def build_model(params: SceneParams | None = None) -> UltrasoundModel:
         link_ids.append(b)
         prev = b
     hand = add_body(prev, p.hand_pos, p.hand_quat, p.hand_mass, (0, 0, 0), np.eye(3) * p.hand_diaginertia)
-    probe_c = np.array([0.0, 0.0, 0.5 * (p.probe_tip_z + p.probe_back_z)])
-    probe_hl = 0.5 * abs(p.probe_tip_z - p.probe_back_z)
-    probe = add_body(
-        hand,
-        p.probe_pos,
-        (1, 0, 0, 0),
-        p.probe_mass,
-        probe_c,
-        capsule_inertia(p.probe_mass, p.probe_radius, probe_hl),
-    )
+    probe_seg, probe_c, probe_I = probe_geometry(p)
+    probe = add_body(hand, p.probe_pos, (1, 0, 0, 0), p.probe_mass, probe_c, probe_I)
 
     npart = 0
     if p.soft_torso:
@@ -410,7 +417,7 @@ def build_model(params: SceneParams | None = None) -> UltrasoundModel:
 
     # ------------------------------------------------------------------ geoms
     # capsule geoms: body-frame segment endpoints + radius
-    A["probe_seg"] = np.array([[0, 0, p.probe_tip_z], [0, 0, p.probe_back_z]], float)
+    A["probe_seg"] = probe_seg
     A["probe_radius"] = np.array([p.probe_radius])
     if p.soft_torso:
         off = p.cap_radius + p.cap_half_len
@@ -580,9 +587,8 @@ def _arm_tables(model: UltrasoundModel):
     Rh = quat2mat(p.hand_quat)
     ph = np.asarray(p.hand_pos, float)
     pp = ph + Rh @ np.asarray(p.probe_pos, float)  # probe body origin in link-7 frame
-    probe_c_local = np.array([0.0, 0.0, 0.5 * (p.probe_tip_z + p.probe_back_z)])
-    probe_hl = 0.5 * abs(p.probe_tip_z - p.probe_back_z)
-    Iprobe = Rh @ capsule_inertia(p.probe_mass, p.probe_radius, probe_hl) @ Rh.T
+    _, probe_c_local, probe_I = probe_geometry(p)
+    Iprobe = Rh @ probe_I @ Rh.T
     parts = [
         (p.link_mass[6], np.asarray(p.link_com[6], float), np.eye(3) * p.link_diaginertia[6]),
         (p.hand_mass, ph, np.eye(3) * p.hand_diaginertia),

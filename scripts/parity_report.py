@@ -47,12 +47,14 @@ def main():
                 marks[s + 1] = dict(dr.max)
 
         dr, log = compare_rollout(O, env, orcs, acts, on_step=on_step)
-        res[name] = dict(envs=n, steps=log["steps"], env_steps=log["env_steps"], max=dr.max, by_step=marks,
+        res[name] = dict(envs=n, steps=log["steps"], env_steps=log["env_steps"], max=dr.max, max_incl_threshold_steps=log["drift_all"].max,
+                         threshold_env_steps=log["threshold_env_steps"], threshold_events=log["threshold_events"], by_step=marks,
                          done_mismatch=log["done_mismatch"], contact_mismatch=len(log["contact_mismatch"]),
                          terminated=int(log["terminated"].sum()), overflow=env.contact_overflow_count,
                          seconds=round(time.time() - t0, 1))
         print(name, json.dumps({k: float(f"{v:.3g}") for k, v in dr.max.items()}), "done_mismatch", len(log["done_mismatch"]),
-              "contact_mismatch", len(log["contact_mismatch"]), "terminated", int(log["terminated"].sum()), flush=True)
+              "contact_mismatch", len(log["contact_mismatch"]), "threshold env-steps", log["threshold_env_steps"], "of", log["env_steps"],
+              "all:", json.dumps({k: float(f"{v:.2g}") for k, v in log["drift_all"].max.items() if k in ("force_rel", "reward", "dfz_rel", "qvel")}), "terminated", int(log["terminated"].sum()), flush=True)
         env.close()
 
     run("config3_soft_tracking", CC_TRACK, True, args.envs, args.steps, 0, 1, **kw)

@@ -69,16 +69,25 @@ class Drift:
         return self.max.get(k, 0.0)
 
 
-def compare_rollout(O, env, orcs, actions, *, threads=None, check_contacts=True, on_step=None):
-    """Step env (auto_reset off) and the oracles with the same actions [steps][n][adim]; returns (Drift, per-step records).
+def compare_rollout(O, env, orcs, actions, *, threads=None, check_contacts=True, on_step=None, settle=5):
+    """Step env (auto_reset off) and the oracles with the same actions [steps][n][adim]; returns (Drift, log).
 
     Compared per step, for every env still running on both sides: qpos, qvel, all 19 observation channels, reward, done,
     the task record entries, contact-pair lists.  Force-like channels are reported as absolute AND relative deviations
-    (relative to max(1 N, |oracle|))."""
+    (relative to max(1 N, |oracle|)).
+
+    The two trajectories run freely from identical initial states, so they are NOT in identical states later (fp32 drift ~1e-5 m):
+    a contact whose distance crosses zero within that drift appears one step apart on the two sides.  The contact's damping force
+    is there from its first step (aref = -B v), so for that step -- and while the kick decays, `settle` steps -- forces differ by
+    O(B v m) although both sides are right.  Such env-steps are the ones where the two contact lists differ (only in pairs within
+    2e-6 m of the threshold: anything else is logged as a mismatch); they are counted (`log["threshold_env_steps"]`) and kept out of
+    the returned Drift, which covers every other env-step; `log["drift_all"]` covers all of them."""
     n = len(orcs)
-    dr = Drift()
-    log = {"done_mismatch": [], "contact_mismatch": [], "steps": 0, "env_steps": 0, "terminated": np.zeros(n, bool)}
+    dr, dr_all = Drift(), Drift()
+    log = {"done_mismatch": [], "contact_mismatch": [], "steps": 0, "env_steps": 0, "terminated": np.zeros(n, bool),
+           "threshold_env_steps": 0, "threshold_events": 0, "drift_all": dr_all}
     alive = np.ones(n, bool)
+    last_event = np.full(n, -10 ** 9)
     jr = np.asarray(env.model.g_jnt_range, dtype=np.float64)
     for s, a in enumerate(actions):
         if not alive.any():
@@ -94,18 +103,34 @@ def compare_rollout(O, env, orcs, actions, *, threads=None, check_contacts=True,
             ncon, g1, g2, _ = [x.cpu().numpy() for x in env.contacts()]
         for i in idx:
             oq, ov, _, ot = orcs[i].get_state()
-            dr.add("qpos", np.abs(q[i] - oq).max())
-            dr.add("qvel", np.abs(v[i] - ov).max())
-            dr.add("reward", abs(r[i] - orr[i]))
-            for name, sl in OBS_GROUPS.items():
-                dr.add("obs_" + name, np.abs(o[i, sl] - oo[i, sl]).max())
-            dr.add("force_rel", (np.abs(o[i, 0:3] - oo[i, 0:3]) / np.maximum(1.0, np.abs(oo[i, 0:3]).max())).max())
-            dr.add("torque_rel", (np.abs(o[i, 3:6] - oo[i, 3:6]) / np.maximum(0.1, np.abs(oo[i, 3:6]).max())).max())
-            dr.add("fz_mean_rel", abs(o[i, 9] - oo[i, 9]) / max(1.0, abs(oo[i, 9] + 5.0)))
-            dr.add("dfz_rel", abs(o[i, 10] - oo[i, 10]) / max(500.0, abs(oo[i, 10])))  # dFz = dF * control_freq: 1 N of force = 500 units
-            for name, k, w in (("traj_pt", abi.TS_TRAJ_PT, 3), ("vel_mean", abi.TS_VEL_MEAN, 1), ("fz_mean", abi.TS_FZ_MEAN, 1),
-                               ("pos_err", abi.TS_POS_ERR, 2), ("ori_err", abi.TS_ORI_ERR, 1)):
-                dr.add("ts_" + name, np.abs(t[i, k:k + w] - ot[k:k + w]).max())
+            if check_contacts:
+                k = int(ncon[i])
+                got = list(zip(g1[i, :k].tolist(), g2[i, :k].tolist()))
+                c = orcs[i].contacts()
+                want = list(zip(c["geom1"].tolist(), c["geom2"].tolist()))
+                if got != want:
+                    last_event[i] = s
+                    log["threshold_events"] += 1
+                    dist = {p: dd for p, dd in zip(want, c["dist"])}
+                    bad = [p for p in set(got) ^ set(want) if abs(dist.get(p, 0.0)) > 2e-6]
+                    order_ok = [p for p in got if p in dist] == [p for p in want if p in set(got)]
+                    if bad or not order_ok or len([p for p in got if p not in dist]) > 2:
+                        log["contact_mismatch"].append(dict(step=s, env=int(i), bad=bad))
+            clean = s - last_event[i] > settle
+            log["threshold_env_steps"] += not clean
+            for D in ((dr, dr_all) if clean else (dr_all,)):
+                D.add("qpos", np.abs(q[i] - oq).max())
+                D.add("qvel", np.abs(v[i] - ov).max())
+                D.add("reward", abs(r[i] - orr[i]))
+                for name, sl in OBS_GROUPS.items():
+                    D.add("obs_" + name, np.abs(o[i, sl] - oo[i, sl]).max())
+                D.add("force_rel", (np.abs(o[i, 0:3] - oo[i, 0:3]) / np.maximum(1.0, np.abs(oo[i, 0:3]).max())).max())
+                D.add("torque_rel", (np.abs(o[i, 3:6] - oo[i, 3:6]) / np.maximum(0.1, np.abs(oo[i, 3:6]).max())).max())
+                D.add("fz_mean_rel", abs(o[i, 9] - oo[i, 9]) / max(1.0, abs(oo[i, 9] + 5.0)))
+                D.add("dfz_rel", abs(o[i, 10] - oo[i, 10]) / max(500.0, abs(oo[i, 10])))  # dFz = dF * control_freq: 1 N of force = 500 units
+                for name, kk, wd in (("traj_pt", abi.TS_TRAJ_PT, 3), ("vel_mean", abi.TS_VEL_MEAN, 1), ("fz_mean", abi.TS_FZ_MEAN, 1),
+                                     ("pos_err", abi.TS_POS_ERR, 2), ("ori_err", abi.TS_ORI_ERR, 1)):
+                    D.add("ts_" + name, np.abs(t[i, kk:kk + wd] - ot[kk:kk + wd]).max())
             exact = (t[i, abi.TS_TOUCHED] == ot[abi.TS_TOUCHED] and t[i, abi.TS_TIMESTEP] == ot[abi.TS_TIMESTEP] and
                      t[i, abi.TS_IN_CONTACT] == ot[abi.TS_IN_CONTACT])
             fg = termination_flags(q[i, :7], t[i], jr, env.horizon)
@@ -113,17 +138,6 @@ def compare_rollout(O, env, orcs, actions, *, threads=None, check_contacts=True,
             if bool(d[i]) != bool(od[i]) or fg != fo or not exact:
                 log["done_mismatch"].append(dict(step=s, env=int(i), gpu=(bool(d[i]),) + fg, oracle=(bool(od[i]),) + fo,
                                                  margin=termination_margin(oq[:7], ot, jr)))
-            if check_contacts:
-                k = int(ncon[i])
-                got = list(zip(g1[i, :k].tolist(), g2[i, :k].tolist()))
-                c = orcs[i].contacts()
-                want = list(zip(c["geom1"].tolist(), c["geom2"].tolist()))
-                if got != want:
-                    dist = {p: dd for p, dd in zip(want, c["dist"])}
-                    bad = [p for p in set(got) ^ set(want) if abs(dist.get(p, 0.0)) > 2e-6]
-                    order_ok = [p for p in got if p in dist] == [p for p in want if p in set(got)]
-                    if bad or not order_ok:
-                        log["contact_mismatch"].append(dict(step=s, env=int(i), bad=bad))
             log["env_steps"] += 1
             if d[i] or od[i]:
                 alive[i] = False

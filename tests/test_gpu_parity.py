@@ -21,7 +21,8 @@ pytestmark = pytest.mark.gpu
 
 def _make(n, soft, cc, **kw):
     from rui_b200.env import BatchedUltrasound
-    return BatchedUltrasound(n, device=0, soft_torso=soft, controller_configs=cc, control_freq=500, horizon=kw.pop("horizon", 1000), **kw)
+    return BatchedUltrasound(n, device=0, soft_torso=soft, controller_configs=cc, control_freq=kw.pop("control_freq", 500),
+                             horizon=kw.pop("horizon", 1000), **kw)
 
 
 def _oracle_from_gpu(O, env, soft, cc, i, **kw):
@@ -97,22 +98,31 @@ def test_config2_rigid_press_trajectory_parity(O):
         oq, ov, _, _ = orc.get_state()
         dq, dv = np.abs(q[0].cpu().numpy() - oq).max(), np.abs(v[0].cpu().numpy() - ov).max()
         drift.append((dq, dv))
-        assert dq <= 1e-4 and dv <= 1e-3, (s, dq, dv)
-        assert abs(float(r[0]) - orr) <= 5e-2 and bool(d[0]) == od
+        assert dq <= 2e-5 and dv <= 2e-4, (s, dq, dv)
+        assert abs(float(r[0]) - orr) <= 5e-3 and bool(d[0]) == od
+        og = o[0].cpu().numpy().astype(np.float64)
+        np.testing.assert_allclose(og[[6, 7, 8, 11, 12, 13, 14, 15, 16, 17, 18]], oo[[6, 7, 8, 11, 12, 13, 14, 15, 16, 17, 18]], atol=2e-4)  # eef velocity, pose error
+        assert np.abs(og[3:6] - oo[3:6]).max() <= 2e-3 * np.abs(oo[3:6]).max() + 1e-3, (s, og[3:6], oo[3:6])  # F/T torque
         assert _contact_lists_match(env, orc, 0), s
         if orc.ncon:
             contact_steps += 1
             if contact_steps > 5:
-                assert abs(float(o[0, 2]) - oo[2]) <= 1e-2 * abs(oo[2]) + 5e-2, (s, float(o[0, 2]), oo[2])
+                assert np.abs(o[0, :3].cpu().numpy() - oo[:3]).max() <= 2e-3 * np.abs(oo[:3]).max() + 1e-2, (s, o[0, :3], oo[:3])
+                assert abs(float(o[0, 9]) - oo[9]) <= 2e-3 * abs(oo[9] + 5) + 1e-2 and abs(float(o[0, 10]) - oo[10]) <= 2e-3 * abs(oo[10]) + 5.0
         if s in (0, 249, 499):  # every env started identically and received the same actions: bit-identical rows
             assert bool((q == q[0]).all()) and bool((v == v[0]).all()) and bool((o[:, :9] == o[0, :9]).all())  # (trajectories differ per env)
     assert contact_steps > 20  # the press really reached the table
     env.close()
 
 
-# Tolerances of the free-running comparison (soft scene, tracking controller, random gains).  PROVISIONAL until measured.
-TOL_SOFT = dict(qpos=1e-5, qvel=5e-4, reward=2e-2, force_rel=1e-3, torque_rel=2e-3, obs_eef_vel=5e-4, fz_mean_rel=1e-3, dfz_rel=1e-3,
-                obs_vel_mean=1e-4, obs_pos_err=1e-5, obs_quat_err=1e-5, ts_traj_pt=1e-6, ts_pos_err=1e-3, ts_ori_err=1e-5)
+# Tolerances of the free-running comparison (soft scene, random actions), each 3-4x the maximum measured on a B200 over 64 envs x 300
+# steps (profiles/r02_parity_drift.json, `max`: qpos 8.2e-6, qvel 3.3e-4, reward 2.1e-2, force 2.1e-3 rel, torque 4.7e-3 rel, eef
+# velocity 1.2e-4, Fz mean 3.3e-3 rel, dFz 4.5e-3 rel, pose error 5.4e-6 / 5.9e-6).  force_rel: |dF| / max(1 N, |F|); torque_rel:
+# / max(0.1 Nm, |T|); dfz_rel: / max(500, |dFz|) (dFz = dF x 500 Hz).  They hold on every env-step whose contact lists agree on the
+# two sides (parity_util.compare_rollout); TOL_ALL bounds the remaining ones, where a contact crosses zero distance one step apart.
+TOL_SOFT = dict(qpos=3e-5, qvel=1.2e-3, reward=6e-2, force_rel=8e-3, torque_rel=1.5e-2, obs_eef_vel=4e-4, fz_mean_rel=1e-2, dfz_rel=1.5e-2,
+                obs_vel_mean=2e-5, obs_pos_err=2e-5, obs_quat_err=2e-5, ts_traj_pt=1e-7, ts_pos_err=4e-3, ts_ori_err=1e-3)
+TOL_ALL = dict(qpos=3e-5, qvel=3e-3, force_rel=0.3, obs_pos_err=2e-5, obs_quat_err=2e-5)
 
 
 def _assert_drift(dr, tol, where=""):
@@ -138,6 +148,8 @@ def test_config3_soft_sweep_parity_all_channels(O):
     dr, log = compare_rollout(O, env, orcs, acts)
     assert log["steps"] == steps and log["env_steps"] == n * steps
     _assert_drift(dr, TOL_SOFT, "config 3")
+    _assert_drift(log["drift_all"], TOL_ALL, "config 3, env-steps with a contact on the threshold")
+    assert log["threshold_env_steps"] <= 0.08 * log["env_steps"], log["threshold_env_steps"]  # measured 3.4 %
     assert not log["done_mismatch"], log["done_mismatch"][:3]
     assert len(log["contact_mismatch"]) == 0, log["contact_mismatch"][:3]
     assert env.contact_overflow_count == 0 and env.divergence_count == 0
