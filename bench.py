@@ -335,12 +335,96 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+def run_ppo(args):
+    """--workload ppo: BASELINE config 5 -- PPO training from rl_config.yaml hyper-parameters on GPU-batched rollouts, one process
+    per GPU, envs sharded over the ranks, gradients averaged by one flat NCCL all-reduce per minibatch.  One bench "step" = one PPO
+    iteration = a rollout of n_steps control steps of every env + n_epochs x minibatches optimiser steps."""
+    import torch
+    import torch.distributed as dist
+
+    from rui_b200.env import BatchedUltrasound
+    from rui_b200.ppo import PPO
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    per_gpu = args.envs or 8192  # config 5 at 8 GPUs: 65536 envs
+    opts = dict(ENV_OPTS, early_termination=True)  # rl_config.yaml:53
+    env = BatchedUltrasound(per_gpu, device=dev, seed=SEED, env_id_offset=rank * per_gpu, **opts)
+    n_steps = args.n_steps
+    model = PPO(env, n_steps=n_steps, seed=SEED, net_arch=[dict(pi=[256, 128], vf=[256, 128])])  # rl_config.yaml:13-16
+    model.profile_allreduce = world > 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model._setup()
+    for _ in range(max(args.warmup, 3)):  # includes the CUDA-graph capture of the minibatch step
+        model.train(model.collect_rollouts())
+    model.allreduce_ms()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = env.launch_count
+    e0, e1, em = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), []
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        batch = model.collect_rollouts()
+        m = torch.cuda.Event(enable_timing=True)
+        m.record()
+        em.append(m)
+        model.train(batch)
+    e1.record()
+    barrier()
+    clocks = sampler.result()
+    ms = e0.elapsed_time(e1)
+    ar_ms, ar_n = model.allreduce_ms()
+    t = torch.tensor([ms, ar_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, ar_max = [float(x) for x in t.tolist()]
+    total = per_gpu * world * n_steps * args.steps
+    if rank == 0:
+        nmb = (per_gpu * n_steps) // model.batch_size
+        line = {
+            "metric": "ultrasound env-steps/sec", "value": total / (ms_max * 1e-3), "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 5: PPO training (rl_config.yaml hyper-parameters) on {per_gpu * world} GPU-batched envs, "
+                                   f"{world} GPU(s), NCCL gradient all-reduce",
+                       "envs_total": per_gpu * world, "envs_per_gpu": per_gpu, "n_steps": n_steps,
+                       "n_steps_note": "the reference's 2048 x 64 envs; 2048 x 65536 would exceed total_timesteps (SURVEY 8d cfg 5)",
+                       "n_epochs": model.n_epochs, "minibatches_per_epoch": nmb, "batch_size_per_gpu": model.batch_size,
+                       "bench_step": "one PPO iteration: rollout (n_steps control steps of every env) + update",
+                       "early_termination": True, "policy": "MlpPolicy pi/vf [256,128] (76,941 parameters), random init",
+                       "l2": "rollout buffers (19 obs x n_steps x envs) exceed nothing relevant; not flushed"},
+            "clocks": clocks, "gpu_launches": int(env.launch_count - l0),
+            "ppo": {"allreduce_ms_per_iteration": ar_max / args.steps, "allreduces_per_iteration": ar_n / max(args.steps, 1),
+                    "allreduce_bytes": 4 * sum(p.numel() for p in model.policy.parameters()),
+                    "step_reward_mean": model.last_stats.get("step_reward_mean"), "ep_len_mean": model.last_stats.get("ep_len_mean")},
+            "e2e": {"value": total / (ms_max * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "training keeps observations, actions and rewards on the device: there is no host hop in this workload"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="env", choices=["env", "ppo"], help="env: the env step (configs 3/4, default); ppo: config 5")
+    ap.add_argument("--n-steps", type=int, default=32, help="--workload ppo: rollout length per PPO iteration")
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: BASELINE configs)")
     ap.add_argument("--iters", type=int, default=40, help="solver iteration cap")
     ap.add_argument("--rebuilds", type=int, default=0, help="preconditioner rebuilds allowed per solve (0: library default)")
@@ -357,6 +441,8 @@ def main():
         ENV_OPTS["early_termination"] = True
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "ppo":
+        run_ppo(args)
     else:
         run_cuda(args)
 

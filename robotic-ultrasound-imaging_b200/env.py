@@ -634,6 +634,7 @@ class UltrasoundVecEnv:
             opts["scene_params"] = cylinder_torso_params()
         self.core = BatchedUltrasound(num_envs, device=device, seed=seed, env_id_offset=env_id_offset, **opts)
         self.num_envs = num_envs
+        self.seed_value = int(seed)
         low, high = self.core.action_spec
         self.action_space = _Box(low.astype(np.float32), high.astype(np.float32))
         self.observation_space = _Box(-np.inf, np.inf, (OBS_DIM,), np.float32)
@@ -641,6 +642,9 @@ class UltrasoundVecEnv:
         self._t0 = time.time()
         self._ep_ret = np.zeros(num_envs, np.float64)
         self._ep_len = np.zeros(num_envs, np.int64)
+        self._ep_hist_r: List[List[float]] = [[] for _ in range(num_envs)]  # Monitor.get_episode_rewards / _lengths
+        self._ep_hist_l: List[List[int]] = [[] for _ in range(num_envs)]
+        self._views: Optional[List[_EnvView]] = None
 
     def reset(self) -> np.ndarray:
         self._ep_ret[:] = 0
@@ -659,6 +663,8 @@ class UltrasoundVecEnv:
         for i in np.nonzero(done)[0]:
             infos[i]["terminal_observation"] = tobs[i].copy()
             infos[i]["episode"] = {"r": float(self._ep_ret[i]), "l": int(self._ep_len[i]), "t": round(time.time() - self._t0, 6)}
+            self._ep_hist_r[i].append(float(self._ep_ret[i]))
+            self._ep_hist_l[i].append(int(self._ep_len[i]))
             self._ep_ret[i] = 0
             self._ep_len[i] = 0
         return obs, rew, done, infos
@@ -670,17 +676,144 @@ class UltrasoundVecEnv:
     def close(self):
         self.core.close()
 
+    # -- the rest of SB3's VecEnv surface (rl.py never calls these; SB3's own wrappers and utilities do) ----------------
+    def _view(self, i):
+        if self._views is None:
+            self._views = [_EnvView(self, k) for k in range(self.num_envs)]
+        return self._views[i]
+
+    def _idx(self, indices):
+        if indices is None:
+            return list(range(self.num_envs))
+        return [indices] if isinstance(indices, int) else list(indices)
+
     def seed(self, seed=None):
-        return [None] * self.num_envs
+        return [self._view(i).seed(None if seed is None else seed + i)[0] for i in range(self.num_envs)]
 
-    def get_attr(self, name, indices=None):
-        return [getattr(self.core, name)] * self.num_envs
+    def get_attr(self, attr_name, indices=None):
+        return [getattr(self._view(i), attr_name) for i in self._idx(indices)]
 
-    def set_attr(self, name, value, indices=None):
-        raise NotImplementedError("per-env attributes are fixed at construction")
+    def set_attr(self, attr_name, value, indices=None):
+        if attr_name in ("horizon", "control_freq", "action_dim", "action_spec", "observation_space", "action_space"):
+            raise AttributeError(f"{attr_name} is fixed at construction of the batched env")
+        for i in self._idx(indices):
+            setattr(self._view(i), attr_name, value)
 
-    def env_method(self, method_name, *args, indices=None, **kwargs):
-        raise NotImplementedError(method_name)
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        return [getattr(self._view(i), method_name)(*method_args, **method_kwargs) for i in self._idx(indices)]
 
     def env_is_wrapped(self, wrapper_class, indices=None):
-        return [False] * self.num_envs
+        return [getattr(wrapper_class, "__name__", "") == "Monitor"] * len(self._idx(indices))
+
+
+# ----------------------------------------------------------------------------
+# stable-baselines3 adapter (rl.py:130,140,143: SubprocVecEnv -> VecNormalize -> PPO)
+# ----------------------------------------------------------------------------
+def _gym_box(low, high, shape=None):
+    """``gym.spaces.Box`` when gym / gymnasium is installed (SB3 type-checks its spaces), else the stand-in."""
+    for mod in ("gym", "gymnasium"):
+        try:
+            spaces = __import__(mod + ".spaces", fromlist=["Box"])
+        except ImportError:
+            continue
+        if shape is not None:
+            return spaces.Box(low=low, high=high, shape=shape, dtype=np.float32)
+        return spaces.Box(low=np.asarray(low, np.float32), high=np.asarray(high, np.float32), dtype=np.float32)
+    return _Box(low, high, shape, np.float32)
+
+
+class _EnvView:
+    """What ``get_attr`` / ``env_method`` see as "env i" of the vectorised env: the GymWrapper-level attributes of rl.py's workers."""
+
+    def __init__(self, vec: "UltrasoundVecEnv", index: int):
+        self._vec, self.index = vec, index
+        c = vec.core
+        self.horizon, self.control_freq, self.action_dim = c.horizon, c.control_freq, c.action_dim
+        self.action_spec = c.action_spec
+        self.observation_space, self.action_space = vec.observation_space, vec.action_space
+        self.reward_range = (0.0, 12.0)  # ultrasound.py:230-269: five terms, maxima 5 + 1 + 1 + 3 + 2
+        self.spec, self.metadata, self.render_mode = None, {"render.modes": []}, None
+
+    def seed(self, seed=None):
+        """GymWrapper.seed (rl.py:40).  The device streams are keyed by (seed, global env id, episode) at construction."""
+        return [self._vec.seed_value + self.index if seed is None else seed]
+
+    def get_episode_rewards(self):  # Monitor
+        return list(self._vec._ep_hist_r[self.index])
+
+    def get_episode_lengths(self):  # Monitor
+        return list(self._vec._ep_hist_l[self.index])
+
+    def get_state(self):
+        """(qpos, qvel) of this env (mujoco-py ``sim.get_state()``-like, numpy)"""
+        q, v, _, _ = self._vec.core.get_state()
+        return q[self.index].cpu().numpy(), v[self.index].cpu().numpy()
+
+
+def sb3_vec_env_class():
+    """``class SB3UltrasoundVecEnv(stable_baselines3.common.vec_env.VecEnv)``, created on demand: stable-baselines3 is not a
+    dependency of this package (and is not installed where the tests run), so the subclass exists only when SB3 imports.
+    An instance passes SB3's ``isinstance(env, VecEnv)`` checks (``VecNormalize(env)``, ``PPO("MlpPolicy", env)``, rl.py:140-143),
+    carries gym ``Box`` spaces, auto-resets with ``terminal_observation`` / Monitor ``episode`` infos, and implements the whole
+    abstract surface (``get_attr / set_attr / env_method / env_is_wrapped / seed``)."""
+    from stable_baselines3.common.vec_env import VecEnv  # ImportError if SB3 is absent: the caller decides
+
+    class SB3UltrasoundVecEnv(VecEnv):
+        def __init__(self, num_envs: int, env_options: Optional[Dict[str, Any]] = None, seed: int = 0, device=0, env_id_offset: int = 0):
+            self._impl = UltrasoundVecEnv(num_envs, env_options, seed=seed, device=device, env_id_offset=env_id_offset)
+            lo, hi = self._impl.core.action_spec
+            VecEnv.__init__(self, num_envs, _gym_box(-np.inf, np.inf, (OBS_DIM,)), _gym_box(lo, hi))
+            self._impl.observation_space, self._impl.action_space = self.observation_space, self.action_space
+            self._views = [_EnvView(self._impl, i) for i in range(num_envs)]
+            self._overlay: List[Dict[str, Any]] = [{} for _ in range(num_envs)]
+
+        # -- the abstract surface of VecEnv ---------------------------------
+        def reset(self):
+            return self._impl.reset()
+
+        def step_async(self, actions):
+            self._impl.step_async(actions)
+
+        def step_wait(self):
+            return self._impl.step_wait()
+
+        def close(self):
+            self._impl.close()
+
+        def _idx(self, indices):
+            if indices is None:
+                return list(range(self.num_envs))
+            return [indices] if isinstance(indices, int) else list(indices)
+
+        def get_attr(self, attr_name, indices=None):
+            return [self._overlay[i][attr_name] if attr_name in self._overlay[i] else getattr(self._views[i], attr_name) for i in self._idx(indices)]
+
+        def set_attr(self, attr_name, value, indices=None):
+            # per-env Python-side attributes only: anything that shapes the device step is fixed at construction
+            if attr_name in ("horizon", "control_freq", "action_dim", "action_spec", "observation_space", "action_space"):
+                raise AttributeError(f"{attr_name} is fixed at construction of the batched env")
+            for i in self._idx(indices):
+                self._overlay[i][attr_name] = value
+
+        def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+            return [getattr(self._views[i], method_name)(*method_args, **method_kwargs) for i in self._idx(indices)]
+
+        def env_is_wrapped(self, wrapper_class, indices=None):
+            # the batched env itself provides what rl.py:39 wraps around each worker: Monitor episode statistics
+            return [getattr(wrapper_class, "__name__", "") == "Monitor"] * len(self._idx(indices))
+
+        def seed(self, seed=None):
+            return [v.seed(None if seed is None else seed + i)[0] for i, v in enumerate(self._views)]
+
+        def get_images(self):
+            raise NotImplementedError("rendering is out of scope of the hot path")
+
+        def render(self, mode="human"):
+            raise NotImplementedError("rendering is out of scope of the hot path")
+
+    return SB3UltrasoundVecEnv
+
+
+def make_sb3_vec_env(num_envs: int, env_options: Optional[Dict[str, Any]] = None, seed: int = 0, device=0, env_id_offset: int = 0):
+    """Drop-in for ``SubprocVecEnv([make_robosuite_env(...)] * num_cpu)`` of rl.py:130 when stable-baselines3 is installed."""
+    return sb3_vec_env_class()(num_envs, env_options, seed=seed, device=device, env_id_offset=env_id_offset)

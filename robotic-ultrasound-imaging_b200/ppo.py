@@ -196,6 +196,9 @@ class PPO:
         self.ep_len = torch.zeros(self.N, dtype=torch.float64, device=self.device)
         self.last_stats: Dict[str, float] = {}
         self._last_obs = None
+        # opt-in device timing of the NCCL gradient all-reduce (bench.py --workload ppo): pairs of CUDA events, drained by allreduce_ms()
+        self.profile_allreduce = False
+        self._ar_events = []
 
     # ------------------------------------------------------------------ rollouts
     def _setup(self):
@@ -262,6 +265,23 @@ class PPO:
             n = g.numel()
             g.copy_(flat[off:off + n].view_as(g))
             off += n
+
+    def _timed_allreduce(self, flat):
+        if self.profile_allreduce:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            e1.record()
+            self._ar_events.append((e0, e1))
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+
+    def allreduce_ms(self):
+        """(total device ms, count) of the gradient all-reduces timed since the last call (profile_allreduce)."""
+        torch.cuda.synchronize(self.device)
+        ms, n = sum(a.elapsed_time(b) for a, b in self._ar_events), len(self._ar_events)
+        self._ar_events = []
+        return ms, n
 
     def _minibatch_loss(self, obs, act, old_lp, adv, ret):
         a = (adv - adv.mean()) / (adv.std() + 1e-8)
@@ -339,7 +359,7 @@ class PPO:
                 g["idx"].copy_(perm[s:s + self.batch_size])
                 g["a"].replay()
                 if self.world > 1:
-                    dist.all_reduce(g["flat"], op=dist.ReduceOp.SUM)
+                    self._timed_allreduce(g["flat"])
                 g["b"].replay()
             self._n_updates += 1
         pl, vl, kl = (float(t) for t in g["stats"])

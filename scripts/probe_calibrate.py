@@ -76,9 +76,70 @@ def show(name, s):
           f"tq_free {f(s['tq_free_mean'])} tq_c_mean {f(s['tq_contact_mean'])} tq_c_std {f(s['tq_contact_std'])} Fz(depth) {f(s['fz_by_depth'])}", flush=True)
 
 
+def loss(s, ref):
+    """weighted squared mismatch of the summary statistics (log ratios for positive quantities)"""
+    L = 0.0
+    lr = lambda a, b: np.log(max(a, 1e-3) / max(b, 1e-3))
+    L += 4 * ((s["contact_frac"] - ref["contact_frac"]) / 0.05) ** 2
+    L += ((s["onset_z"] - ref["onset_z"]) / 0.002) ** 2
+    for k in ("fz_median", "fz_mean", "fz_max", "fx_std", "fy_std"):
+        L += (lr(s[k], ref[k]) / 0.2) ** 2
+    L += 2 * (lr(s["lat_ratio_median"], ref["lat_ratio_median"]) / 0.2) ** 2
+    for a, b in zip(s["fz_by_depth"], ref["fz_by_depth"]):
+        if a is not None and b is not None:
+            L += 0.5 * (lr(a, b) / 0.25) ** 2
+    L += ((s["fx_over_fz"] - ref["fx_over_fz"]) / 0.04) ** 2 + ((s["fy_over_fz"] - ref["fy_over_fz"]) / 0.04) ** 2
+    for a, b in zip(s["tq_free_mean"] or [0, 0, 0], ref["tq_free_mean"]):
+        L += ((a - b) / 0.01) ** 2
+    for a, b in zip(s["tq_contact_mean"], ref["tq_contact_mean"]):
+        L += ((a - b) / 0.05) ** 2
+    for a, b in zip(s["tq_contact_std"], ref["tq_contact_std"]):
+        L += (lr(a, b) / 0.25) ** 2
+    return float(L)
+
+
+def unpack(x):
+    """x = [ax, ay, az, bx, by, bz, radius, cx, cy, cz]"""
+    return dict(probe_seg_a=tuple(x[0:3]), probe_seg_b=tuple(x[3:6]), probe_radius=float(x[6]), probe_com=tuple(x[7:10]))
+
+
+def fit(ref, starts, iters, log_path):
+    from scipy.optimize import minimize
+    base = SceneParams()
+    best = (1e30, None, None)
+    hist = []
+
+    def f(x):
+        nonlocal best
+        if not (0.003 <= x[6] <= 0.07) or np.abs(x[:6]).max() > 0.15 or np.abs(x[7:10]).max() > 0.2 or np.linalg.norm(x[0:3] - x[3:6]) < 1e-3:
+            return 1e6
+        try:
+            st = stats(reset_rows(dataclasses.replace(base, **unpack(x))))
+            L = loss(st, ref)
+        except Exception:
+            return 1e6
+        hist.append((L, x.tolist()))
+        if L < best[0]:
+            best = (L, x.copy(), st)
+            show(f"L={L:8.2f}", st)
+            print("   x =", np.round(x, 4).tolist(), flush=True)
+            with open(log_path, "w") as fh:
+                json.dump(dict(loss=L, x=x.tolist(), params={k: (list(v) if isinstance(v, tuple) else v) for k, v in unpack(x).items()},
+                               stats=st, art=ref, evaluations=len(hist)), fh, indent=1)
+        return L
+
+    for x0 in starts:
+        x0 = np.asarray(x0, float)
+        step = np.array([0.01] * 6 + [0.004] + [0.01] * 3)
+        simplex = np.vstack([x0] + [x0 + step * e for e in np.eye(10)])
+        minimize(f, x0, method="Nelder-Mead", options=dict(maxfev=iters, initial_simplex=simplex, xatol=2e-4, fatol=1e-2))
+    return best
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--fit", type=int, default=0, help="Nelder-Mead evaluations per start")
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
     ref = stats(art_rows())
@@ -92,6 +153,15 @@ def main():
         out["candidates"][name] = dict(params={k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()}, stats=s)
 
     ev("shipped SceneParams")
+    print("loss of the shipped parameters:", round(loss(out["candidates"]["shipped SceneParams"]["stats"], ref), 2))
+    if args.fit:
+        starts = json.loads(os.environ.get("PROBE_STARTS", "[]")) or [
+            [0, 0, -0.05, 0, 0, -0.10, 0.05, 0, 0, -0.075],              # round-1 axial capsule
+            [0.02, 0.0, -0.012, -0.02, 0.0, -0.012, 0.012, 0, 0.015, -0.05],   # bar across body x
+            [0.0, 0.02, -0.012, 0.0, -0.02, -0.020, 0.012, 0, 0.015, -0.05],   # tilted bar across body y
+        ]
+        fit(ref, starts, args.fit, args.json or os.path.join(ROOT, "gpurun_out", "probe_fit.json"))
+        return
     if args.sweep:
         for cand in json.loads(os.environ.get("PROBE_CANDIDATES", "[]")):
             nm = cand.pop("name")

@@ -413,6 +413,14 @@ def main():
     np.savez_compressed(os.path.join(OUT, "tracking_policy.npz"), **{k: v.numpy() for k, v in sd.items()},
                         obs_mean=np.array(art["tracking"]["obs_mean"]), obs_var=np.array(art["tracking"]["obs_var"]))
     print("wrote art_stats.json:", {k: (v["num_timesteps"], len(v["ep_returns"])) for k, v in art.items()})
+    # the in-tree MJCF scene files, parsed by the package's own reader (robotic-ultrasound-imaging_b200/mjcf.py): SceneParams is
+    # asserted against this parse (tests/test_task_golden.py::test_scene_params_match_the_reference_mjcf)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from rui_b200 import mjcf
+    models = os.path.join(REF, "my_models")
+    with open(os.path.join(OUT, "mjcf_golden.json"), "w") as f:
+        json.dump({"soft_box": mjcf.read_assets(models, True), "soft_human_torso": mjcf.read_assets(models, False)}, f, indent=1)
+    print("wrote mjcf_golden.json")
 
 
 if __name__ == "__main__":

@@ -219,3 +219,71 @@ def test_committed_bench_lines_follow_the_contract():
             assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] > 0
     ref = json.loads(open(os.path.join(ROOT, "profiles", "r01_bench_reference_arm.json")).read().strip().splitlines()[-1])
     assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "port"
+
+
+def _fake_sb3(monkeypatch):
+    """stable-baselines3 is not installed here: a stand-in package with the ABSTRACT surface of SB3 1.1's
+    ``stable_baselines3.common.vec_env.base_vec_env.VecEnv`` (the class ``VecNormalize`` / ``PPO`` type-check against)."""
+    import abc
+    import sys
+    import types
+
+    class VecEnv(abc.ABC):
+        metadata = {"render.modes": ["human", "rgb_array"]}
+
+        def __init__(self, num_envs, observation_space, action_space):
+            self.num_envs, self.observation_space, self.action_space = num_envs, observation_space, action_space
+
+        @abc.abstractmethod
+        def reset(self): ...
+        @abc.abstractmethod
+        def step_async(self, actions): ...
+        @abc.abstractmethod
+        def step_wait(self): ...
+        @abc.abstractmethod
+        def close(self): ...
+        @abc.abstractmethod
+        def get_attr(self, attr_name, indices=None): ...
+        @abc.abstractmethod
+        def set_attr(self, attr_name, value, indices=None): ...
+        @abc.abstractmethod
+        def env_method(self, method_name, *method_args, indices=None, **method_kwargs): ...
+        @abc.abstractmethod
+        def env_is_wrapped(self, wrapper_class, indices=None): ...
+        @abc.abstractmethod
+        def seed(self, seed=None): ...
+
+        def step(self, actions):
+            self.step_async(actions)
+            return self.step_wait()
+
+    pkg, common, vec = types.ModuleType("stable_baselines3"), types.ModuleType("stable_baselines3.common"), types.ModuleType("stable_baselines3.common.vec_env")
+    vec.VecEnv = VecEnv
+    pkg.common, common.vec_env = common, vec
+    for name, mod in (("stable_baselines3", pkg), ("stable_baselines3.common", common), ("stable_baselines3.common.vec_env", vec)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    return VecEnv
+
+
+def test_sb3_adapter_is_a_real_vecenv_subclass(monkeypatch):
+    """rl.py:130-143 hands the vectorised env to SB3's ``VecNormalize`` and ``PPO``, which check ``isinstance(env, VecEnv)``.  The
+    adapter class is created against whatever ``stable_baselines3`` is importable; it must implement the whole abstract surface."""
+    from rui_b200 import env as E
+    base = _fake_sb3(monkeypatch)
+    cls = E.sb3_vec_env_class()
+    assert issubclass(cls, base) and not getattr(cls, "__abstractmethods__", None), cls.__abstractmethods__
+    for m in ("reset", "step_async", "step_wait", "step", "close", "get_attr", "set_attr", "env_method", "env_is_wrapped", "seed"):
+        assert callable(getattr(cls, m))
+    # the stand-alone VecEnv-shaped class (no SB3 needed) has the same method set
+    for m in ("reset", "step_async", "step_wait", "step", "close", "get_attr", "set_attr", "env_method", "env_is_wrapped", "seed"):
+        assert callable(getattr(E.UltrasoundVecEnv, m))
+
+
+def test_sb3_adapter_needs_sb3():
+    """without stable-baselines3 the adapter raises ImportError (the VecEnv-shaped class and the built-in PPO remain)"""
+    import importlib.util
+    if importlib.util.find_spec("stable_baselines3") is not None:
+        pytest.skip("stable-baselines3 is installed")
+    from rui_b200 import env as E
+    with pytest.raises(ImportError):
+        E.sb3_vec_env_class()

@@ -167,3 +167,35 @@ def test_oracle_step_returns_the_observation_reward_was_computed_from(O, soft_mo
         o, r, d = e.step(rng.uniform(0, 1, 6))
         inc = bool(e.get_state()[3][abi.TS_IN_CONTACT])
         assert abs(r - _reward_from_obs_row(O, o, inc)) < 2e-5, s  # (acos near -1 amplifies the 1e-8 norm error of the 8-digit goal_quat)
+
+
+def test_scene_params_match_the_reference_mjcf():
+    """SceneParams (what the kernels are compiled against) vs the reference's in-tree MJCF (soft_box.xml, soft_human_torso.xml,
+    ultrasound_arena.xml + ultrasound_arena.py placement, ultrasound_probe_gripper.xml), parsed by the package's own reader.  The
+    committed parse (tests/golden/mjcf_golden.json, written by make_golden.py) is checked always; where the reference checkout is
+    present the files are re-read and must give the same parse."""
+    import json
+    import os
+
+    from rui_b200 import mjcf
+    from rui_b200.model import SceneParams, cylinder_torso_params
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "mjcf_golden.json")) as f:
+        gold = json.load(f)
+
+    def norm(x):  # JSON turns tuples into lists
+        return json.loads(json.dumps(x))
+
+    for key, params, box in (("soft_box", SceneParams(), True), ("soft_human_torso", cylinder_torso_params(), False)):
+        assert mjcf.check_scene_params(params, gold[key]) == {}, key
+        f = mjcf.scene_fields(gold[key])
+        assert f["comp_count"] == (9, 4, 11) and f["solref_smooth"] == (-1324.17, -17.59) and f["probe_pos"] == (-0.004, -0.063, 0.128)
+        ref = "/root/reference/src/my_models"
+        if os.path.isdir(ref):
+            assert norm(mjcf.read_assets(ref, box)) == gold[key]
+            assert mjcf.scene_params_from_mjcf(ref, box) == params
+    # a deliberately wrong constant is caught
+    import dataclasses
+    assert "cap_radius" in mjcf.check_scene_params(dataclasses.replace(SceneParams(), cap_radius=0.008), gold["soft_box"])
+    assert gold["soft_box"]["gripper"]["mesh_file"] == "meshes/ultrasound_probe_mesh.stl"  # (missing from the reference: A-PROBE-1)
+    assert gold["soft_box"]["arena"]["colliding_geoms"] == ["floor", "table_collision"]
