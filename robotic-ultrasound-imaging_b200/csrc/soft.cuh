@@ -50,6 +50,9 @@
 #ifndef ARM_SHIFT
 #define ARM_SHIFT 1
 #endif
+#ifndef WARP_SOLVE
+#define WARP_SOLVE 0 // 1: dense blocks of the preconditioner solved by one warp with shuffles (chol7_solve_warp2) instead of replicated in every thread.  Measured at 4096 envs: 0.441 ms vs 0.4245 ms replicated -- ~150 instead of ~290 instructions, but the 28 dependent shuffles are the longer chain and the kernel is latency bound: not kept
+#endif
 #ifndef NORESTART
 #define NORESTART 1 // 1: keep the Polak-Ribiere direction across a preconditioner rebuild (flexible CG: beta uses the previous pg, made with the previous preconditioner) instead of restarting; measured 0.464 ms vs 0.485 ms
 #endif
@@ -96,6 +99,7 @@ struct __align__(16) WS {
   // landing zones of the warp reductions, one per call site, one row per warp (readers add the rows in a fixed order: rd())
   float r3[WPE][24], rg[WPE][16], rp[WPE][16], rq[WPE][8], rl[2][WPE][4], rb1[WPE][24], rb2[WPE][24], rb3[WPE][24];
   float lsign[7], lD[7], laref[7];
+  float yS[8];                                         // torso part of P^-1 grad (world frame), warp 0 -> all threads
   float Dt, areft;
   int ncon, okf;
   int consume;                                         // this env's episode ended and a prepared reset slot takes over (K9 -> all threads)
@@ -282,6 +286,35 @@ __device__ __forceinline__ void chol7_solve(const float* L, float* x) {
     for (int k = i + 1; k < N; k++) t -= L[k * 7 + i] * x[k];
     x[i] = t * L[i * 7 + i];
   }
+}
+
+// x <- (L L^T)^-1 b for TWO factors written by chol7_warp2, at once, by one warp: lane r (0..6) holds entry r of the right-hand side of
+// A0, lane 8 + r that of A1; the solution entry comes back in the same lane.  Column-oriented substitution: one broadcast shuffle and
+// one FMA per column (28 shuffles in all) instead of the ~290 replicated, fully unrolled instructions of chol7_solve<7> + <6> in every
+// thread -- the loop body of the solver has to fit the 32 KB instruction cache.
+__device__ __forceinline__ float chol7_solve_warp2(const float* A0, const float* A1, float b, int lane) {
+  const int base = lane & 8, r = lane & 7;
+  const float* A = base ? A1 : A0;
+  const bool act = lane < 16 && r < 7;
+  float Lr[7], Lc[7]; // row r of L left of the diagonal, column r below it (zero elsewhere: no predicates in the loops)
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    Lr[k] = (act && k < r) ? A[r * 7 + k] : 0.f;
+    Lc[k] = (act && k > r) ? A[k * 7 + r] : 0.f;
+  }
+  const float dinv = act ? A[r * 7 + r] : 1.f;
+  if (!act) b = 0.f;
+#pragma unroll
+  for (int j = 0; j < 7; j++) { // L y = b
+    if (r == j) b *= dinv;
+    b -= Lr[j] * __shfl_sync(0xffffffffu, b, base + j);
+  }
+#pragma unroll
+  for (int j = 6; j >= 0; j--) { // L^T x = y
+    if (r == j) b *= dinv;
+    b -= Lc[j] * __shfl_sync(0xffffffffu, b, base + j);
+  }
+  return b;
 }
 
 // Launch slots are ordered longest-solve-first: every launch files its envs into NBIN bins by the number of CG iterations they
@@ -819,6 +852,23 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
     // (fp32 floor of the gradient is ~eps * (|Hx| + |rhs|): the terms that cancel in it)
     gnorm = sqrtf(rd(w.rp, 10));
     if (gnorm <= dm.tol * (1.f + rhsn + hxn)) return false;
+#if WARP_SOLVE
+    // dense blocks: the first warp solves both at once (arm 7x7 in lanes 0-6, torso 6x6 in lanes 8-13); the arm part goes straight to
+    // pg, the torso part (world frame) to yS for everybody; the other warp goes ahead with the stencil pass, which needs neither
+    if (wrp == 0) {
+      const int k = lane & 7;
+      float rhs = 0.f;
+      if (lane < 7) rhs = w.grad[lane];
+      else if (dm.soft && lane >= 8 && lane < 11) // gd[7+k] - (m R t[0:3] + t[3:6])_k
+        rhs = w.grad[7 + k] - (mp * (w.R[3 * k] * rd(w.rp, 0) + w.R[3 * k + 1] * rd(w.rp, 1) + w.R[3 * k + 2] * rd(w.rp, 2)) + rd(w.rp, 3 + k));
+      else if (dm.soft && lane >= 11 && lane < 14) // (R gd[10:13])_k - t[6:9]_k
+        rhs = w.R[3 * (k - 3)] * w.grad[10] + w.R[3 * (k - 3) + 1] * w.grad[11] + w.R[3 * (k - 3) + 2] * w.grad[12] - rd(w.rp, 3 + k);
+      const float sol = chol7_solve_warp2(w.Pa, w.Sf, rhs, lane);
+      if (lane < 7) w.pg[lane] = sol;
+      else if (lane >= 8 && lane < 14) w.yS[k] = dm.soft ? sol : 0.f;
+    }
+    float b[6] = {0, 0, 0, 0, 0, 0};
+#else
     float gd[13]; // dense part of the gradient
 #pragma unroll
     for (int k = 0; k < 13; k++) gd[k] = w.grad[k];
@@ -847,6 +897,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
         b[0] += gd[7] * y[0] + gd[8] * y[1] + gd[9] * y[2] + gd[10] * yb.x + gd[11] * yb.y + gd[12] * yb.z;
       }
     }
+#endif
 #if PREC3
     PRAGMA_HOT
     for (int i = tid; i < np; i += NT) {
@@ -855,7 +906,23 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
                  w.Dp[e.z >> 16] * w.hs[13 + (e.z & 0x7fff)] + w.Dp[e.w >> 16] * w.hs[13 + (e.w & 0x7fff)];
       w.pg[13 + i] = nb * w.dg[i];
     }
+#endif
+#if WARP_SOLVE || PREC3
     env_sync();
+#endif
+#if WARP_SOLVE
+    float y[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) y[k] = w.yS[k];
+    const v3 yl = mtv(R, mk(y[0], y[1], y[2]));
+    if (tid < 13) { // dense part of pg (the torso rotation goes back to the body frame) and its share of grad.pg
+      float pgk;
+      if (tid < 7) pgk = w.pg[tid];
+      else if (tid < 10) pgk = y[0] * (tid == 7) + y[1] * (tid == 8) + y[2] * (tid == 9);
+      else { const int c = tid - 10; pgk = w.R[c] * y[3] + w.R[3 + c] * y[4] + w.R[6 + c] * y[5]; }
+      if (tid >= 7) w.pg[tid] = dm.soft ? pgk : 0.f;
+      if (tid < 7 || dm.soft) b[0] += w.grad[tid] * pgk;
+    }
 #endif
     PRAGMA_HOT
     for (int i = tid; i < np; i += NT) {

@@ -23,7 +23,7 @@ CC = dict(type="OSC_POSE", input_max=1, input_min=-1, output_max=[0.05] * 3 + [0
           damping_ratio=1, impedance_mode="tracking", kp_limits=[0, 500], kp_input_max=1, kp_input_min=0, uncouple_pos_ori=True)
 
 
-def run(envs=4096, steps=3000, deterministic=False, seed=3, device=0):
+def run(envs=4096, steps=3000, deterministic=False, seed=3, device=0, scene_params=None):
     fix = np.load(os.path.join(ROOT, "tests", "golden", "tracking_policy.npz"))
     art = json.load(open(os.path.join(ROOT, "tests", "golden", "art_stats.json")))["tracking"]
     dev = torch.device(f"cuda:{device}")
@@ -32,7 +32,7 @@ def run(envs=4096, steps=3000, deterministic=False, seed=3, device=0):
     mean = torch.as_tensor(fix["obs_mean"], dtype=torch.float32, device=dev)
     std = torch.sqrt(torch.as_tensor(fix["obs_var"], dtype=torch.float32, device=dev) + 1e-8)
     env = BatchedUltrasound(envs, device=dev, controller_configs=CC, control_freq=500, horizon=1000, early_termination=True,
-                            torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=seed)
+                            torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=seed, scene_params=scene_params)
     obs = env.reset().clone()
     reset_obs = obs.clone()
     torch.manual_seed(seed)
@@ -84,8 +84,17 @@ if __name__ == "__main__":
     ap.add_argument("--envs", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--json", default="")
+    ap.add_argument("--probe-json", default="", help="SceneParams overrides (a scripts/probe_calibrate.py --fit result, or a plain dict)")
     a = ap.parse_args()
-    out = run(a.envs, a.steps)
+    sp = None
+    if a.probe_json:
+        import dataclasses
+
+        from rui_b200.model import SceneParams
+        ov = json.load(open(a.probe_json))
+        ov = ov.get("params", ov)
+        sp = dataclasses.replace(SceneParams(), **{k: (tuple(v) if isinstance(v, list) else v) for k, v in ov.items()})
+    out = run(a.envs, a.steps, scene_params=sp)
     names = ["Fx", "Fy", "Fz", "tq_x", "tq_y", "tq_z", "vx", "vy", "vz", "Fz_mean-5", "dFz", "vel_mean-.04", "ex", "ey", "ez", "q0", "q1", "q2", "q3"]
     print(f"{'channel':14s} {'mean':>10s} {'ART mean':>10s} {'var':>12s} {'ART var':>12s}")
     for i, nme in enumerate(names):
@@ -94,5 +103,8 @@ if __name__ == "__main__":
               "reset_pos_err_mean", "reset_pos_err_std"):
         print(f"{k:28s} ours {out[k]}   ART {out['art_' + k]}")
     print("episodes finished:", out["episodes"])
+    rat = lambda x, y: float("nan") if y == 0 else x / y
+    print("ratios ours / ART  mean:", " ".join(f"{nme}={rat(out['obs_mean'][i], out['art_obs_mean'][i]):.2f}" for i, nme in enumerate(names[:6])))
+    print("ratios ours / ART   var:", " ".join(f"{nme}={rat(out['obs_var'][i], out['art_obs_var'][i]):.2f}" for i, nme in enumerate(names[:12])))
     if a.json:
         json.dump(out, open(a.json, "w"), indent=1)

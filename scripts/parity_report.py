@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--envs", type=int, default=64)
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "parity_drift.json"))
+    ap.add_argument("--tol", type=float, default=0.0, help="device solver tolerance (0: library default)")
+    ap.add_argument("--only", default="", help="run only the cases whose name contains this")
     args = ap.parse_args()
     from oracle import oracle as O
     from rui_b200.env import BatchedUltrasound
@@ -34,6 +36,10 @@ def main():
     kw = dict(torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=3)
 
     def run(name, cc, soft, n, steps, lo, hi, adim=6, **extra):
+        if args.only and args.only not in name:
+            return
+        if args.tol:
+            extra["solver_tolerance"] = args.tol
         t0 = time.time()
         env = BatchedUltrasound(n, device=0, soft_torso=soft, controller_configs=cc, **{"control_freq": 500, "horizon": 1000, **extra})
         env.reset()
@@ -58,10 +64,25 @@ def main():
         env.close()
 
     run("config3_soft_tracking", CC_TRACK, True, args.envs, args.steps, 0, 1, **kw)
+    if args.only and "long" in args.only:  # bounded drift beyond the short horizon (north_star): a full 1000-step episode
+        run("long_1000_steps", CC_TRACK, True, 8, 1000, 0, 1, **kw)
     run("config3_early_termination", CC_TRACK, True, args.envs, 250, 0, 1, early_termination=True, **dict(kw, horizon=250))
     run("substeps_5_control_freq_100", CC_TRACK, True, 8, 30, 0, 1, **dict(kw, control_freq=100))
     run("substeps_25_control_freq_20", CC_TRACK, True, 8, 12, 0, 1, **dict(kw, control_freq=20))
-    run("config2_rigid_fixed", CC_FIXED, False, 16, 300, -1, 1)
+    run("config2_rigid_fixed_random", CC_FIXED, False, 16, 300, -1, 1)
+    # BASELINE config 2 proper: press on the table, then random actions (the sequence of tests/test_gpu_parity.py)
+    if not args.only or args.only in "config2_rigid_press":
+        from test_gpu_parity import _config2_actions
+        env = BatchedUltrasound(64, device=0, soft_torso=False, controller_configs=CC_FIXED, control_freq=500, horizon=1000)
+        env.reset()
+        orcs = make_oracles(O, env, CC_FIXED, n=1, soft=False)
+        dr, log = compare_rollout(O, env, orcs, _config2_actions(64))
+        res["config2_rigid_press"] = dict(envs=64, steps=log["steps"], max=dr.max, max_incl_threshold_steps=log["drift_all"].max,
+                                          threshold_env_steps=log["threshold_env_steps"], done_mismatch=log["done_mismatch"],
+                                          contact_mismatch=len(log["contact_mismatch"]))
+        print("config2_rigid_press", json.dumps({k: float(f"{v:.3g}") for k, v in dr.max.items()}), "threshold env-steps", log["threshold_env_steps"],
+              "all:", json.dumps({k: float(f"{v:.2g}") for k, v in log["drift_all"].max.items() if k in ("force_rel", "reward", "qvel", "qpos")}), flush=True)
+        env.close()
     run("wrench", dict(CC_TRACK, impedance_mode="wrench"), True, 8, 60, -10, 10, **kw)
     run("variable_z", dict(CC_TRACK, impedance_mode="variable_z"), True, 8, 60, np.r_[np.zeros(6), -1], np.ones(7), adim=7, **kw)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)

@@ -80,8 +80,8 @@ def loss(s, ref):
     """weighted squared mismatch of the summary statistics (log ratios for positive quantities)"""
     L = 0.0
     lr = lambda a, b: np.log(max(a, 1e-3) / max(b, 1e-3))
-    L += 4 * ((s["contact_frac"] - ref["contact_frac"]) / 0.05) ** 2
-    L += ((s["onset_z"] - ref["onset_z"]) / 0.002) ** 2
+    L += 8 * ((s["contact_frac"] - ref["contact_frac"]) / 0.05) ** 2
+    L += 4 * ((s["onset_z"] - ref["onset_z"]) / 0.002) ** 2
     for k in ("fz_median", "fz_mean", "fz_max", "fx_std", "fy_std"):
         L += (lr(s[k], ref[k]) / 0.2) ** 2
     L += 2 * (lr(s["lat_ratio_median"], ref["lat_ratio_median"]) / 0.2) ** 2

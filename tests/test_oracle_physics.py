@@ -456,3 +456,34 @@ def test_probe_contact_force_observation_is_the_sum_of_its_contact_forces(O, sof
         assert abs(e.get_state()[3][abi.TS_FZ_MEAN] - fz_mean) < 1e-9
         seen += np.abs(F).max() > 1.0
     assert seen >= 10  # the probe really presses on the torso
+
+
+def test_arm_links_stay_clear_of_torso_and_table(O, soft_model):
+    """Assumption A-COLL-2: the robosuite Panda link / mount collision geoms (contype 1, SURVEY App. B.1 last row) are
+    not built -- only the probe collides.  The task keeps the probe pressed on the torso top with the arm reaching over it from the
+    mount at x = -0.56: over random-gain episodes every link segment (joint origin to joint origin, a generous 8 cm collision
+    radius) stays well clear of the torso's box and of the table top, so those geoms could never produce a contact here."""
+    m = soft_model.model
+    ids = m.ids
+    link0, hand = int(ids[2]), int(ids[3])
+    half = np.array([0.175, 0.14, 0.0525]) + 0.0075  # world half-extents of the composite box (SURVEY App. B.2) + capsule radius
+    rng = np.random.default_rng(3)
+    worst_torso, worst_table = np.inf, np.inf
+    for seed in (3, 4):
+        e = O.OracleEnv(soft_model, _cfg(CC_TRACK, seed=seed, torso_solref_randomization=True, initial_probe_pos_randomization=True), seed)
+        e.reset()
+        for s in range(120):
+            e.step(rng.uniform(0, 1, 6))
+            if s % 10:
+                continue
+            q = e.get_state()[0]
+            xpos, _ = forward_kinematics(m, q)
+            centre = q[7:10]
+            pts = [xpos[b] for b in range(link0, hand + 1)]  # link 1..7 origins + hand
+            for a, b in zip(pts[:-2], pts[1:-1]):  # segments up to link 7 (the last one carries the probe, which does collide)
+                for t in np.linspace(0, 1, 9):
+                    p = a + t * (b - a)
+                    d = np.maximum(np.abs(p - centre) - half, 0)
+                    worst_torso = min(worst_torso, np.linalg.norm(d) - 0.08)
+                    worst_table = min(worst_table, p[2] - 0.8 - 0.08)
+    assert worst_torso > 0.05 and worst_table > 0.05, (worst_torso, worst_table)
