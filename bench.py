@@ -303,7 +303,7 @@ def run_cuda(args):
                        "early_termination": ENV_OPTS["early_termination"],
                        "episode_phase": f"uniformly random per env + {preroll} untimed pre-roll steps (steady-state mix of resets and "
                                         "post-reset transients; independent of --steps/--warmup)",
-                       "solver": f"PCG cap {args.iters}, relative gradient tolerance {args.tol or 1e-5:g}", "mean_ncon": mean_ncon, "mean_solver_iters": mean_iters,
+                       "solver": f"PCG cap {args.iters}, relative gradient tolerance {args.tol or 3e-5:g}", "mean_ncon": mean_ncon, "mean_solver_iters": mean_iters,
                        "l2": "state (~27 MB at 4096 envs) is smaller than L2; 256 MiB memset between steps, outside the per-step events"
                              if flush is not None else "not flushed"},
             "clocks": clocks,
@@ -428,7 +428,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: BASELINE configs)")
     ap.add_argument("--iters", type=int, default=40, help="solver iteration cap")
     ap.add_argument("--rebuilds", type=int, default=0, help="preconditioner rebuilds allowed per solve (0: library default)")
-    ap.add_argument("--tol", type=float, default=0.0, help="device solver tolerance (0: library default 1e-5)")
+    ap.add_argument("--tol", type=float, default=0.0, help="device solver tolerance (0: library default 3e-5)")
     ap.add_argument("--preroll", type=int, default=-1, help="untimed steps after randomising the episode phases (-1: one horizon)")
     ap.add_argument("--early-termination", action="store_true", help="rl_config.yaml:53 (episodes then last tens of steps under random actions)")
     ap.add_argument("--no-flush", action="store_true")

@@ -77,6 +77,7 @@ enum {
  * replaces robosuite's XML merge + MuJoCo's compiler, ultrasound.py:272-321). */
 typedef struct usim_model {
   int32_t nbody, nq, nv, npart, npair, soft;
+  int32_t narm, reserved0; /* real arm joints: 7 (Panda) or 6 (UR5e: the seventh arm slot is an inert, decoupled degree of freedom) */
   int32_t table_body, link1_body, hand_body, probe_body, torso_body, part_body0;
   /* generic kinematic tree (oracle / invweight computation) */
   const int32_t *body_parent, *body_jnt_type, *body_qposadr, *body_dofadr; /* [nbody] */

@@ -36,6 +36,7 @@ _pi = C.POINTER(C.c_int32)
 class UsimModel(C.Structure):
     _fields_ = [
         ("nbody", C.c_int32), ("nq", C.c_int32), ("nv", C.c_int32), ("npart", C.c_int32), ("npair", C.c_int32), ("soft", C.c_int32),
+        ("narm", C.c_int32), ("reserved0", C.c_int32),
         ("table_body", C.c_int32), ("link1_body", C.c_int32), ("hand_body", C.c_int32), ("probe_body", C.c_int32),
         ("torso_body", C.c_int32), ("part_body0", C.c_int32),
         ("body_parent", _pi), ("body_jnt_type", _pi), ("body_qposadr", _pi), ("body_dofadr", _pi),
@@ -83,6 +84,7 @@ class PackedModel:
         ids = model.ids
         s.nbody, s.nq, s.nv = model.nbody, model.nq, model.nv
         s.npart, s.npair, s.soft = int(ids[7]), len(model.eq_pairs), int(p.soft_torso)
+        s.narm = len(p.link_pos)
         s.table_body, s.link1_body, s.hand_body, s.probe_body = int(ids[1]), int(ids[2]), int(ids[3]), int(ids[4])
         s.torso_body, s.part_body0 = int(ids[5]), int(ids[6])
 
@@ -113,7 +115,7 @@ class PackedModel:
         s.solref_smooth[:] = p.solref_smooth
         s.table_top_z, s.table_half_xy, s.table_friction = p.table_top_z, p.table_half_xy, p.table_friction
         s.probe_friction, s.particle_friction = p.probe_friction, p.particle_friction
-        s.init_qpos[:] = p.init_qpos
+        s.init_qpos[:] = tuple(p.init_qpos) + (0.0,) * (7 - len(p.init_qpos))
         s.top_torso_offset, s.traj_x_range, s.traj_y_range = p.top_torso_offset, p.traj_x_range, p.traj_y_range
         self.struct = s
 
@@ -140,7 +142,7 @@ def make_config(
     seed: int = 0,
     env_id_offset: int = 0,
     solver_iterations: int = 40,
-    solver_tolerance: float = 1e-5,
+    solver_tolerance: float = 3e-5,
     precond_rebuilds: int = 0,
     ignore_done: bool = False,
     reset_eef_bias=ART_RESET_EEF_BIAS,

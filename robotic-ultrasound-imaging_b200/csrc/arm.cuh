@@ -6,6 +6,8 @@
 #pragma once
 #include "common.cuh"
 
+// NJ = number of real arm joints: 7 (Panda) or 6 (UR5e).  Every per-env array keeps 7 slots; with NJ = 6 the seventh is an inert,
+// decoupled degree of freedom (unit inertia, no Jacobian column, no torque), so the solve kernel and the state layout do not change.
 struct ArmKin {
   float R[7][9];  // link frames
   v3 p[7];        // link origins == joint anchors
@@ -14,11 +16,12 @@ struct ArmKin {
   float Rs[9];    // site orientation
 };
 
+template <int NJ>
 __device__ __forceinline__ void arm_fk(const float* q, ArmKin& k) {
   float Rp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   v3 pp = mk(0, 0, 0);
 #pragma unroll
-  for (int j = 0; j < 7; j++) {
+  for (int j = 0; j < NJ; j++) {
     k.p[j] = pp + mv(Rp, ld3(dm.link_pos[j]));
     float T[9], Rz[9];
     mm3(Rp, dm.link_R[j], T);
@@ -31,18 +34,24 @@ __device__ __forceinline__ void arm_fk(const float* q, ArmKin& k) {
     for (int i = 0; i < 9; i++) Rp[i] = k.R[j][i];
     pp = k.p[j];
   }
-  k.site = k.p[6] + mv(k.R[6], ld3(dm.tool + 0));
-  mm3(k.R[6], dm.tool + 3, k.Rs);
-  k.hand = k.p[6] + mv(k.R[6], ld3(dm.tool + 12));
+  k.site = k.p[NJ - 1] + mv(k.R[NJ - 1], ld3(dm.tool + 0));
+  mm3(k.R[NJ - 1], dm.tool + 3, k.Rs);
+  k.hand = k.p[NJ - 1] + mv(k.R[NJ - 1], ld3(dm.tool + 12));
 }
 
-// J[6][7]: rows 0-2 linear, 3-5 angular, of world point x on link 7
+// J[6][7]: rows 0-2 linear, 3-5 angular, of world point x on the last link (columns of absent joints are zero)
+template <int NJ>
 __device__ __forceinline__ void arm_jac(const ArmKin& k, v3 x, float* J) {
 #pragma unroll
   for (int j = 0; j < 7; j++) {
-    v3 jp = cross(k.z[j], x - k.p[j]);
-    J[0 * 7 + j] = jp.x; J[1 * 7 + j] = jp.y; J[2 * 7 + j] = jp.z;
-    J[3 * 7 + j] = k.z[j].x; J[4 * 7 + j] = k.z[j].y; J[5 * 7 + j] = k.z[j].z;
+    if (j < NJ) {
+      v3 jp = cross(k.z[j], x - k.p[j]);
+      J[0 * 7 + j] = jp.x; J[1 * 7 + j] = jp.y; J[2 * 7 + j] = jp.z;
+      J[3 * 7 + j] = k.z[j].x; J[4 * 7 + j] = k.z[j].y; J[5 * 7 + j] = k.z[j].z;
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; r++) J[r * 7 + j] = 0.f;
+    }
   }
 }
 
@@ -87,19 +96,20 @@ __device__ __forceinline__ void osc_set_goal(const float* act, const ArmKin& k, 
 // (q, qd: the arm joint positions / velocities of this env, in registers: the caller may have just written them to HBM itself)
 // policy_step: first physics substep of a control step -- the only one on which the OSC goal is set (robosuite Robot.control)
 // ts / ab: the env's task record and arm record; act: the env's action row
+template <int NJ>
 __device__ __forceinline__ void arm_forward(int mode, bool policy_step, const float (&q)[7], const float (&qd)[7],
                                             const float* __restrict__ act, float* __restrict__ ts, float* __restrict__ ab) {
   if (mode == 0 && ts[USIM_TS_DONE] != 0.f) return; // terminated env: frozen until reset
 
   ArmKin k;
-  arm_fk(q, k);
+  arm_fk<NJ>(q, k);
 
   // ---------------- velocities, velocity-product accelerations (gravity folded in: a_base = -g), world frame
   v3 w[7], al[7], ac[7]; // angular vel, angular acc (vp), linear acc of the link origin (vp, with -g)
   {
     v3 wp = mk(0, 0, 0), alp = mk(0, 0, 0), acp = mk(-dm.g[0], -dm.g[1], -dm.g[2]), pp = mk(0, 0, 0);
 #pragma unroll
-    for (int j = 0; j < 7; j++) {
+    for (int j = 0; j < NJ; j++) {
       v3 r = k.p[j] - pp;
       v3 zq = qd[j] * k.z[j];
       ac[j] = acp + cross(alp, r) + cross(wp, cross(wp, r));
@@ -110,12 +120,16 @@ __device__ __forceinline__ void arm_forward(int mode, bool policy_step, const fl
   }
   // ---------------- RNE backward pass -> bias; CRBA composites -> M
   float bias[7], M[49];
+#pragma unroll
+  for (int i = 0; i < 49; i++) M[i] = (i % 8 == 0) ? 1.f : 0.f; // identity in the slots of absent joints
+#pragma unroll
+  for (int j = 0; j < 7; j++) bias[j] = 0.f;
   {
     v3 F = mk(0, 0, 0), N = mk(0, 0, 0); // accumulated force / moment about p[j+1]
-    v3 pn = k.p[6];
+    v3 pn = k.p[NJ - 1];
     float cm = 0.f; v3 cc = mk(0, 0, 0); float Ic[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // composite mass, com, inertia about com
 #pragma unroll
-    for (int j = 6; j >= 0; j--) {
+    for (int j = NJ - 1; j >= 0; j--) {
       v3 cl = mv(k.R[j], ld3(dm.link_com[j]));
       v3 com = k.p[j] + cl;
       float Iw[9];
@@ -155,8 +169,8 @@ __device__ __forceinline__ void arm_forward(int mode, bool policy_step, const fl
   }
   // ---------------- Jacobians
   float J[42], Jh[42];
-  arm_jac(k, k.site, J);
-  arm_jac(k, k.hand, Jh);
+  arm_jac<NJ>(k, k.site, J);
+  arm_jac<NJ>(k, k.hand, Jh);
 
   // ---------------- OSC_POSE torques [SURVEY App. C.2/C.3]
   float tau[7], dx[7];
@@ -286,19 +300,24 @@ __device__ __forceinline__ void arm_forward(int mode, bool policy_step, const fl
   float tau0[3], Jft[21];
   {
     float Iw[9];
-    world_inertia(k.R[6], dm.tool + 26, Iw);
+    constexpr int LL = NJ - 1; // the link the hand and the probe are welded to
+    world_inertia(k.R[LL], dm.tool + 26, Iw);
     float mp = dm.tool[22];
-    v3 cl = mv(k.R[6], ld3(dm.tool + 23)); // probe COM relative to p[6]
-    v3 rc = k.p[6] + cl - k.site;          // COM relative to the site
-    v3 acom = ac[6] + cross(al[6], cl) + cross(w[6], cross(w[6], cl));
-    v3 t0 = mv(Iw, al[6]) + cross(w[6], mv(Iw, w[6])) + cross(rc, mp * acom);
+    v3 cl = mv(k.R[LL], ld3(dm.tool + 23)); // probe COM relative to p[LL]
+    v3 rc = k.p[LL] + cl - k.site;          // COM relative to the site
+    v3 acom = ac[LL] + cross(al[LL], cl) + cross(w[LL], cross(w[LL], cl));
+    v3 t0 = mv(Iw, al[LL]) + cross(w[LL], mv(Iw, w[LL])) + cross(rc, mp * acom);
     tau0[0] = t0.x; tau0[1] = t0.y; tau0[2] = t0.z;
 #pragma unroll
     for (int j = 0; j < 7; j++) {
-      v3 jr = k.z[j];
-      v3 jp = mk(J[0 * 7 + j], J[1 * 7 + j], J[2 * 7 + j]) + cross(jr, rc); // COM Jacobian column
-      v3 t = mv(Iw, jr) + cross(rc, mp * jp);
-      Jft[0 * 7 + j] = t.x; Jft[1 * 7 + j] = t.y; Jft[2 * 7 + j] = t.z;
+      if (j < NJ) {
+        v3 jr = k.z[j];
+        v3 jp = mk(J[0 * 7 + j], J[1 * 7 + j], J[2 * 7 + j]) + cross(jr, rc); // COM Jacobian column
+        v3 t = mv(Iw, jr) + cross(rc, mp * jp);
+        Jft[0 * 7 + j] = t.x; Jft[1 * 7 + j] = t.y; Jft[2 * 7 + j] = t.z;
+      } else {
+        Jft[0 * 7 + j] = 0.f; Jft[1 * 7 + j] = 0.f; Jft[2 * 7 + j] = 0.f;
+      }
     }
   }
 
@@ -314,8 +333,8 @@ __device__ __forceinline__ void arm_forward(int mode, bool policy_step, const fl
   st3(ab + AB_EEFPOS, k.site);
 #pragma unroll
   for (int i = 0; i < 9; i++) ab[AB_EEFR + i] = k.Rs[i];
-  st3(ab + AB_PTIP, k.p[6] + mv(k.R[6], ld3(dm.tool + 15)));
-  st3(ab + AB_PBACK, k.p[6] + mv(k.R[6], ld3(dm.tool + 18)));
+  st3(ab + AB_PTIP, k.p[NJ - 1] + mv(k.R[NJ - 1], ld3(dm.tool + 15)));
+  st3(ab + AB_PBACK, k.p[NJ - 1] + mv(k.R[NJ - 1], ld3(dm.tool + 18)));
   ab[AB_TAU0] = tau0[0]; ab[AB_TAU0 + 1] = tau0[1]; ab[AB_TAU0 + 2] = tau0[2];
   float qx[4];
   mat2quat_xyzw(k.Rs, qx);
@@ -326,6 +345,7 @@ __device__ __forceinline__ void arm_forward(int mode, bool policy_step, const fl
 
 // One thread per env.  Also clears `done` (frozen envs report done = 0; the solve kernel sets it for the envs it steps), and flattens
 // the iteration-count bins the previous solve launch filled into the launch order of the next one (highest bin first; soft.cuh NBIN).
+template <int NJ>
 __global__ void __launch_bounds__(64) arm_kernel(int n, const float* __restrict__ qpos, const float* __restrict__ qvel,
                                                  const float* __restrict__ act, float* __restrict__ task, float* __restrict__ armbuf,
                                                  uint8_t* __restrict__ done, int policy_step, int nbin, const int* __restrict__ bin_cnt_prev,
@@ -347,7 +367,7 @@ __global__ void __launch_bounds__(64) arm_kernel(int n, const float* __restrict_
   float q[7], qd[7];
 #pragma unroll
   for (int j = 0; j < 7; j++) { q[j] = qpos[(size_t)env * QPAD + j]; qd[j] = qvel[(size_t)env * QPAD + j]; }
-  arm_forward(0, policy_step != 0, q, qd, act + (size_t)env * dm.adim, task + (size_t)env * USIM_TASK_DIM, armbuf + (size_t)env * ARMBUF);
+  arm_forward<NJ>(0, policy_step != 0, q, qd, act + (size_t)env * dm.adim, task + (size_t)env * USIM_TASK_DIM, armbuf + (size_t)env * ARMBUF);
 }
 
 // ---------------------------------------------------------------- reset (ultrasound.py:416-477, :749-887)
@@ -359,6 +379,7 @@ __global__ void __launch_bounds__(64) arm_kernel(int n, const float* __restrict_
 //     the live state; files a request to prepare episode number + 2 into the slot this episode number belongs to.
 //   prepare mode: works through the (env, episode number) requests of `items`; rows go to slot (episode number & 1) of the env
 //     (qpos / task: [2][n][...]), the arm record to row `item` of `armbuf`.  A reset state is at rest: no qvel / warm rows.
+template <int NJ>
 __global__ void __launch_bounds__(32) reset_kernel(int n, const uint8_t* __restrict__ mask, float* __restrict__ qpos, float* __restrict__ qvel,
                                                    float* __restrict__ warm, float* __restrict__ task, float* __restrict__ armbuf,
                                                    const int* __restrict__ items, const int* __restrict__ nitems,
@@ -447,7 +468,7 @@ __global__ void __launch_bounds__(32) reset_kernel(int n, const uint8_t* __restr
     float en_prev = 1e30f;
 #pragma unroll 1
     for (int it = 0; it < 60; it++) {
-      arm_fk(q, k);
+      arm_fk<NJ>(q, k);
       v3 ep3 = target - k.site, eo = ori_error(G, k.Rs);
       float err[6] = {ep3.x, ep3.y, ep3.z, eo.x, eo.y, eo.z};
       float en = sqrtf(dot(ep3, ep3) + dot(eo, eo));
@@ -455,7 +476,7 @@ __global__ void __launch_bounds__(32) reset_kernel(int n, const uint8_t* __restr
       if (en < 2e-6f || (en < 1e-4f && en > 0.5f * en_prev)) break;
       en_prev = en;
       float J[42], A[36];
-      arm_jac(k, k.site, J);
+      arm_jac<NJ>(k, k.site, J);
 #pragma unroll
       for (int a = 0; a < 6; a++)
 #pragma unroll
@@ -483,12 +504,12 @@ __global__ void __launch_bounds__(32) reset_kernel(int n, const uint8_t* __restr
   }
 #pragma unroll
   for (int j = 0; j < 7; j++) { qp[j] = q[j]; ts[USIM_TS_INIT_JOINT + j] = q[j]; }
-  arm_fk(q, k);
+  arm_fk<NJ>(q, k);
   st3(ts + USIM_TS_GOAL_POS, k.site); // osc.reset_goal
 #pragma unroll
   for (int i = 0; i < 9; i++) ts[USIM_TS_GOAL_ORI + i] = k.Rs[i];
   const float qd0[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  arm_forward(1, false, q, qd0, nullptr, ts, ab);
+  arm_forward<NJ>(1, false, q, qd0, nullptr, ts, ab);
   } // work items
 }
 

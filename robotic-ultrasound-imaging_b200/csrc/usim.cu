@@ -31,7 +31,7 @@ static int fail(const std::string& m) {
   } while (0)
 
 struct usim_handle {
-  int device = 0, n = 0, nq = 0, nv = 0, adim = 6, soft = 0, substeps = 1;
+  int device = 0, n = 0, nq = 0, nv = 0, adim = 6, soft = 0, substeps = 1, narm = 7;
   DevModel hm;
   // per-env state, env-major rows (one warp owns one row -> one coalesced 128-B aligned stream)
   float *qpos = nullptr, *qvel = nullptr, *warm = nullptr, *task = nullptr, *armbuf = nullptr, *diag = nullptr;
@@ -95,6 +95,7 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail("usim_create: kernels are built for sm_100a only; found sm_" + std::to_string(prop.major * 10 + prop.minor));
   if (m->soft && (m->npart > NPART_MAX || m->npair > NPAIR_MAX)) return fail("usim_create: composite larger than the compiled limits");
+  if (m->narm != 7 && m->narm != 6) return fail("usim_create: the arm kernels are compiled for 7 (Panda) or 6 (UR5e) joints");
   // physics substeps per control step: int(control_timestep / model_timestep) [robosuite MujocoEnv.step]; 1 at rl_config.yaml's
   // 500 Hz, 25 at the env's own default of 20 Hz (ultrasound.py:119)
   if (!(c->control_freq > 0.0)) return fail("usim_create: control_freq must be positive");
@@ -102,7 +103,7 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   if (substeps < 1) return fail("usim_create: control_freq above 1/timestep (less than one physics step per control step)");
 
   usim_handle* h = new usim_handle();
-  h->device = device; h->n = c->num_envs; h->nq = m->nq; h->nv = m->nv; h->soft = m->soft; h->substeps = substeps;
+  h->device = device; h->n = c->num_envs; h->nq = m->nq; h->nv = m->nv; h->soft = m->soft; h->substeps = substeps; h->narm = m->narm;
   h->adim = c->impedance_mode == USIM_MODE_VARIABLE_Z ? 7 : 6;
   DevModel& d = h->hm;
   memset(&d, 0, sizeof d);
@@ -327,6 +328,18 @@ static int mark_state(usim_handle* h, cudaStream_t s) {
   return 0;
 }
 
+// the arm / reset kernels are compiled per joint count (arm.cuh NJ)
+#define ARM_LAUNCH(h, grid, block, stream, ...)                                                   \
+  do {                                                                                            \
+    if ((h)->narm == 7) arm_kernel<7><<<grid, block, 0, stream>>>(__VA_ARGS__);                   \
+    else arm_kernel<6><<<grid, block, 0, stream>>>(__VA_ARGS__);                                  \
+  } while (0)
+#define RESET_LAUNCH(h, grid, block, stream, ...)                                                 \
+  do {                                                                                            \
+    if ((h)->narm == 7) reset_kernel<7><<<grid, block, 0, stream>>>(__VA_ARGS__);                 \
+    else reset_kernel<6><<<grid, block, 0, stream>>>(__VA_ARGS__);                                \
+  } while (0)
+
 static SolveArgs base_args(usim_handle* h, int mode) {
   SolveArgs a;
   memset(&a, 0, sizeof a);
@@ -355,7 +368,7 @@ static int producer_end(usim_handle* h, cudaStream_t s) {
   int* cnt = h->req_cnt + b;
   CK(cudaEventRecord(h->ev_prod, s));
   CK(cudaStreamWaitEvent(h->prep_stream, h->ev_prod, 0));
-  reset_kernel<<<64, 32, 0, h->prep_stream>>>(n, nullptr, h->slot_qpos, nullptr, nullptr, h->slot_task, h->prep_armbuf, list, cnt, nullptr, nullptr);
+  RESET_LAUNCH(h, 64, 32, h->prep_stream, n, nullptr, h->slot_qpos, nullptr, nullptr, h->slot_task, h->prep_armbuf, list, cnt, nullptr, nullptr);
   SolveArgs a = base_args(h, 1);
   a.prep = 1; a.armbuf = h->prep_armbuf; a.prep_items = list; a.prep_n = cnt;
   a.diag = nullptr; a.ncon_out = nullptr; a.geom1_out = nullptr; a.geom2_out = nullptr; a.dist_out = nullptr;
@@ -377,9 +390,8 @@ static int launch_step(usim_handle* h, const float* act, float* obs, float* rew,
   for (int sub = 0; sub < nsub; sub++) {
     const bool last = sub == nsub - 1;
     const int b = (int)(h->solve_tick & 1); // this launch files into bins b; its order comes from bins 1 - b
-    arm_kernel<<<(n + ARM_BLOCK - 1) / ARM_BLOCK, ARM_BLOCK, 0, s>>>(
-        n, h->qpos, h->qvel, act, h->task, h->armbuf, sub == 0 ? done : nullptr, sub == 0, NBIN, h->bin_cnt + (1 - b) * NBIN,
-        h->bin_items + (size_t)(1 - b) * NBIN * n, h->bin_cnt + b * NBIN, h->order);
+    ARM_LAUNCH(h, (n + ARM_BLOCK - 1) / ARM_BLOCK, ARM_BLOCK, s, n, h->qpos, h->qvel, act, h->task, h->armbuf, sub == 0 ? done : nullptr,
+               sub == 0, NBIN, h->bin_cnt + (1 - b) * NBIN, h->bin_items + (size_t)(1 - b) * NBIN * n, h->bin_cnt + b * NBIN, h->order);
     SolveArgs a = base_args(h, last ? 0 : 2);
     a.obs = obs; a.rew = rew; a.done = done; a.tobs = tobs;
     a.order = h->order; a.bin_cnt = h->bin_cnt + b * NBIN; a.bin_items = h->bin_items + (size_t)b * NBIN * n;
@@ -422,8 +434,8 @@ int usim_reset(usim_handle* h, const uint8_t* mask_dev, float* obs_dev, void* st
     h->launches += 1;
   }
   // the reset itself, in place and in stream order: reset kernel (live mode) + forward-only solve on the live state
-  reset_kernel<<<(n + 31) / 32, 32, 0, s>>>(n, mask_dev, h->qpos, h->qvel, h->warm, h->task, h->armbuf, nullptr, nullptr,
-                                           first ? nullptr : list, first ? nullptr : cnt);
+  RESET_LAUNCH(h, (n + 31) / 32, 32, s, n, mask_dev, h->qpos, h->qvel, h->warm, h->task, h->armbuf, nullptr, nullptr,
+               first ? nullptr : list, first ? nullptr : cnt);
   SolveArgs a = base_args(h, 1);
   a.mask = mask_dev; a.obs = obs_dev;
   solve_kernel<<<n, NT, h->smem, s>>>(a);

@@ -83,7 +83,7 @@ class BatchedUltrasound:
         seed: int = 0,
         env_id_offset: int = 0,
         solver_iterations: int = 40,
-        solver_tolerance: float = 1e-5,
+        solver_tolerance: float = 3e-5,
         scene_params: Optional[SceneParams] = None,
         **cfg_kwargs,
     ):
@@ -291,7 +291,7 @@ class _Robot:
     def __init__(self, env: "Ultrasound"):
         self._env = env
         self.name = env.robot_name
-        self.dof = 7
+        self.dof = len(env.core.model.params.link_pos)  # 7 (Panda) / 6 (UR5e)
         self.init_qpos = np.array(env.core.model.params.init_qpos)
         self.controller = _Controller(env)
         self.robot_model = _RobotModel()
@@ -303,15 +303,15 @@ class _Robot:
 
     @property
     def _joint_positions(self):
-        return self._env.core.get_state()[0][0, :7].cpu().numpy().astype(np.float64)
+        return self._env.core.get_state()[0][0, :self.dof].cpu().numpy().astype(np.float64)
 
     @property
     def _joint_velocities(self):
-        return self._env.core.get_state()[1][0, :7].cpu().numpy().astype(np.float64)
+        return self._env.core.get_state()[1][0, :self.dof].cpu().numpy().astype(np.float64)
 
     @property
     def torques(self):
-        return self._env.core.diag()[0, 13:20].cpu().numpy().astype(np.float64)
+        return self._env.core.diag()[0, 13:13 + self.dof].cpu().numpy().astype(np.float64)
 
     @property
     def ee_torque(self):
@@ -329,13 +329,13 @@ class _Robot:
     def check_q_limits(self) -> bool:
         """robosuite ``Robot.check_q_limits``: any joint within 0.1 rad of a limit (ultrasound.py:651)."""
         q = self._joint_positions
-        rng = np.asarray(self._env.core.model.g_jnt_range, dtype=np.float64)[:7]
+        rng = np.asarray(self._env.core.model.g_jnt_range, dtype=np.float64)[:self.dof]
         return bool(np.any(~((rng[:, 0] + 0.1 < q) & (q < rng[:, 1] - 0.1))))
 
     def set_robot_joint_positions(self, jpos):
         """ultrasound.py:462: overwrite the arm joint positions (velocities are left as they are, as in robosuite)."""
         q = self._env.core.get_state()[0]
-        q[0, :7] = torch.as_tensor(np.asarray(jpos, dtype=np.float32), device=q.device)
+        q[0, :self.dof] = torch.as_tensor(np.asarray(jpos, dtype=np.float32), device=q.device)
         self._env.core.set_state(qpos=q)
 
 
@@ -407,9 +407,9 @@ class Ultrasound:
         self.table_full_size = tuple(table_full_size)
         if scene_params is None and not use_box_torso:
             scene_params = cylinder_torso_params(soft_torso=soft_torso)
-        if robots == "UR5e":
-            raise NotImplementedError("UR5e (ultrasound.py:137,833-839): the kernels are specialised for the 7-DoF Panda chain; "
-                                      "SURVEY §8f rank 2, DESIGN.md §9")
+        if robots == "UR5e":  # ultrasound.py:137,833-839: six joints, the seventh arm slot of the state is inert
+            from .model import ur5e_params
+            scene_params = ur5e_params(scene_params if scene_params is not None else SceneParams(soft_torso=soft_torso))
         self.core = BatchedUltrasound(
             1, device=device, soft_torso=soft_torso, controller_configs=controller_configs, control_freq=control_freq,
             horizon=horizon, early_termination=early_termination, torso_solref_randomization=torso_solref_randomization,
@@ -627,11 +627,17 @@ class UltrasoundVecEnv:
 
     def __init__(self, num_envs: int, env_options: Optional[Dict[str, Any]] = None, seed: int = 0, device=0, env_id_offset: int = 0):
         opts = dict(env_options or {})
-        for k in ("env_id", "robots", "use_camera_obs", "use_object_obs", "has_renderer", "has_offscreen_renderer", "render_camera",
+        robots = opts.pop("robots", "Panda")
+        robots = robots[0] if isinstance(robots, (list, tuple)) else robots
+        assert robots in ("Panda", "UR5e"), "Robot must be either Panda or UR5e!"
+        for k in ("env_id", "use_camera_obs", "use_object_obs", "has_renderer", "has_offscreen_renderer", "render_camera",
                   "camera_names", "camera_heights", "camera_widths", "camera_depths", "reward_shaping", "save_data", "gripper_types"):
             opts.pop(k, None)
         if not opts.pop("use_box_torso", True):
             opts["scene_params"] = cylinder_torso_params()
+        if robots == "UR5e":
+            from .model import ur5e_params
+            opts["scene_params"] = ur5e_params(opts.get("scene_params"))
         self.core = BatchedUltrasound(num_envs, device=device, seed=seed, env_id_offset=env_id_offset, **opts)
         self.num_envs = num_envs
         self.seed_value = int(seed)

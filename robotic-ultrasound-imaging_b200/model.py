@@ -131,7 +131,11 @@ class SceneParams:
     table_half_xy: float = 0.4
     table_friction: float = 1.0
 
-    # ---- Panda [EXT-recall A-PANDA-1]
+    # ---- arm: Panda [EXT-recall A-PANDA-1] by default; `ur5e_params()` swaps in the UR5e chain (6 joints).  One tuple entry per joint.
+    robot: str = "Panda"
+    link_axis: Tuple[Tuple[float, float, float], ...] | None = None  # joint axes in the link frames (None: all local z)
+    link_inertia_quat: Tuple[Tuple[float, float, float, float], ...] | None = None  # orientation of the principal axes (None: link frame)
+    link_diaginertia3: Tuple[Tuple[float, float, float], ...] | None = None  # full principal inertias (None: `link_diaginertia` x identity)
     base_pos: Tuple[float, float, float] = (-0.56, 0.0, 0.913)
     link_pos: Tuple[Tuple[float, float, float], ...] = (
         (0, 0, 0.333),
@@ -291,6 +295,40 @@ def probe_geometry(p: SceneParams):
     return np.array([a, b]), com, Rc @ capsule_inertia(p.probe_mass, p.probe_radius, hl) @ Rc.T
 
 
+def ur5e_params(base: SceneParams | None = None, **kw) -> SceneParams:
+    """`robots="UR5e"` (ultrasound.py:137,833-839,863-864): the robosuite UR5e chain [EXT-recall, assumption A-UR5E-1: robosuite
+    `models/assets/robots/ur5e/robot.xml` -- link offsets, joint axes, inertials, +-150 / +-28 Nm actuators, `init_qpos`, same
+    mount and table offset as the Panda].  Six joints: the seventh arm slot of the state is an inert degree of freedom."""
+    s2 = 0.7071067811865476
+    return dataclasses.replace(
+        base or SceneParams(), robot="UR5e",
+        link_pos=((0, 0, 0.163), (0, 0.138, 0), (0, -0.131, 0.425), (0, 0, 0.392), (0, 0.127, 0), (0, 0, 0.1)),
+        link_quat=((1, 0, 0, 0), (s2, 0, s2, 0), (1, 0, 0, 0), (s2, 0, s2, 0), (1, 0, 0, 0), (1, 0, 0, 0)),
+        link_axis=((0, 0, 1), (0, 1, 0), (0, 1, 0), (0, 1, 0), (0, 0, 1), (0, 1, 0)),
+        link_mass=(3.7, 8.393, 2.33, 1.219, 1.219, 0.1889),
+        link_diaginertia=(0.0, 0.0, 0.0, 0.0, 0.0, 0.0),
+        link_diaginertia3=((0.0102675, 0.0102675, 0.00666), (0.133886, 0.133886, 0.0151074), (0.0312168, 0.0312168, 0.004095),
+                           (0.0025599, 0.0025599, 0.0021942), (0.0025599, 0.0025599, 0.0021942), (0.000132134, 9.90863e-05, 9.90863e-05)),
+        link_inertia_quat=((1, 0, 0, 0),) * 5 + ((s2, 0, 0, s2),),
+        link_com=((0, 0, 0), (0, 0, 0.2125), (0, 0, 0.196), (0, 0.127, 0), (0, 0, 0.1), (0, 0.0771683, 0)),
+        joint_range=((-6.28319, 6.28319), (-6.28319, 6.28319), (-3.14159, 3.14159), (-6.28319, 6.28319), (-6.28319, 6.28319), (-6.28319, 6.28319)),
+        joint_damping=0.001, ctrl_range=(150.0, 150.0, 150.0, 28.0, 28.0, 28.0),
+        init_qpos=(-0.470, -1.735, 2.480, -2.275, -1.590, -1.991),
+        hand_pos=(0.0, 0.098, 0.0), hand_quat=(s2, -s2, 0.0, 0.0), **kw)
+
+
+def _link_inertia(p: SceneParams, j: int):
+    """inertia of arm link j about its COM, in the link frame"""
+    if p.link_diaginertia3 is None:
+        return np.eye(3) * p.link_diaginertia[j]
+    Rq = quat2mat(p.link_inertia_quat[j]) if p.link_inertia_quat is not None else np.eye(3)
+    return Rq @ np.diag(p.link_diaginertia3[j]) @ Rq.T
+
+
+def _link_axis(p: SceneParams, j: int):
+    return np.asarray(p.link_axis[j] if p.link_axis is not None else (0.0, 0.0, 1.0), float)
+
+
 def cylinder_torso_params(**kw) -> SceneParams:
     """`use_box_torso=False`: soft_human_torso.xml:8-14 (composite cylinder, bottom site at -0.05) and ultrasound.py:184-186."""
     return SceneParams(comp_type="cylinder", top_torso_offset=0.041, traj_y_range=0.05, torso_pos=(0.0, 0.0, 0.8 + 0.005 + 0.05), **kw)
@@ -319,22 +357,19 @@ def build_model(params: SceneParams | None = None) -> UltrasoundModel:
     table = add_body(world, (0, 0, p.table_top_z - 0.025), (1, 0, 0, 0), 0, (0, 0, 0), np.zeros((3, 3)))
     prev = world
     link_ids = []
-    for j in range(7):
+    nj = len(p.link_pos)
+    assert nj in (6, 7), "the arm kernels are compiled for 6 or 7 joints"
+    for j in range(nj):
         pos = np.asarray(p.link_pos[j], float)
         if j == 0:
             pos = pos + np.asarray(p.base_pos, float)
-        b = add_body(
-            prev,
-            pos,
-            p.link_quat[j],
-            p.link_mass[j],
-            p.link_com[j],
-            np.eye(3) * p.link_diaginertia[j],
-            JNT_HINGE,
-            (0, 0, 1),
-        )
+        b = add_body(prev, pos, p.link_quat[j], p.link_mass[j], p.link_com[j], _link_inertia(p, j), JNT_HINGE, _link_axis(p, j))
         link_ids.append(b)
         prev = b
+    for j in range(nj, 7):
+        # inert degree of freedom filling the arm's seventh state slot: a unit-inertia rotor on the world, coupled to nothing
+        # (M = 1 on its diagonal, no gravity torque, no Jacobian column, no actuator)
+        add_body(world, (0, 0, -10.0), (1, 0, 0, 0), 1.0, (0, 0, 0), np.eye(3), JNT_HINGE, (0, 0, 1))
     hand = add_body(prev, p.hand_pos, p.hand_quat, p.hand_mass, (0, 0, 0), np.eye(3) * p.hand_diaginertia)
     probe_seg, probe_c, probe_I = probe_geometry(p)
     probe = add_body(hand, p.probe_pos, (1, 0, 0, 0), p.probe_mass, probe_c, probe_I)
@@ -396,12 +431,12 @@ def build_model(params: SceneParams | None = None) -> UltrasoundModel:
     A["g_body_dofadr"] = np.array(dadr, np.int32)
 
     damping = np.zeros(nv)
-    damping[:7] = p.joint_damping
+    damping[:nj] = p.joint_damping
     if p.soft_torso:
         damping[7:13] = p.free_joint_damping
     A["g_dof_damping"] = damping
-    A["g_jnt_range"] = np.array(p.joint_range, float)  # arm only (7,2)
-    A["g_ctrl_range"] = np.array(p.ctrl_range, float)
+    A["g_jnt_range"] = np.array(tuple(p.joint_range) + ((-1e9, 1e9),) * (7 - nj), float)  # arm only (7,2); inert slot: unlimited
+    A["g_ctrl_range"] = np.array(tuple(p.ctrl_range) + (0.0,) * (7 - nj), float)
 
     qpos0 = np.zeros(nq)
     if p.soft_torso:
@@ -572,25 +607,38 @@ def _arm_tables(model: UltrasoundModel):
     """
     p = model.params
     A = model.arrays
+    nj = len(p.link_pos)
     link = np.zeros((7, 22))
-    for j in range(7):
+    link[:, 3:12] = np.eye(3).reshape(9)
+    # The kernels rotate every joint about its frame's z axis.  A joint about another axis a_j is brought to that convention by
+    # re-orienting its frame: F'_j = F_j A_j with A_j z = a_j; everything attached to link j (child offset / orientation, COM,
+    # inertia, tool) is then expressed in the rotated frame, A_j^T (.).
+    Aprev = np.eye(3)
+    Acur = []
+    for j in range(nj):
         pos = np.asarray(p.link_pos[j], float)
         if j == 0:
             pos = pos + np.asarray(p.base_pos, float)
-        link[j, 0:3] = pos
-        link[j, 3:12] = quat2mat(p.link_quat[j]).reshape(9)
-        link[j, 12:15] = p.link_com[j]
+        Aj = quat2mat(z2quat(_link_axis(p, j)))
+        link[j, 0:3] = Aprev.T @ pos
+        link[j, 3:12] = (Aprev.T @ quat2mat(p.link_quat[j]) @ Aj).reshape(9)
+        link[j, 12:15] = Aj.T @ np.asarray(p.link_com[j], float)
         link[j, 15] = p.link_mass[j]
-        d = p.link_diaginertia[j]
-        link[j, 16:22] = [d, d, d, 0, 0, 0]
-    # weld hand + probe into link 7
-    Rh = quat2mat(p.hand_quat)
-    ph = np.asarray(p.hand_pos, float)
-    pp = ph + Rh @ np.asarray(p.probe_pos, float)  # probe body origin in link-7 frame
+        I = Aj.T @ _link_inertia(p, j) @ Aj
+        link[j, 16:22] = [I[0, 0], I[1, 1], I[2, 2], I[0, 1], I[0, 2], I[1, 2]]
+        Acur.append(Aj)
+        Aprev = Aj
+    AL = Acur[-1]
+    # weld hand + probe into the last link (expressed in its rotated frame)
+    Rh = AL.T @ quat2mat(p.hand_quat)
+    ph = AL.T @ np.asarray(p.hand_pos, float)
+    pp = ph + Rh @ np.asarray(p.probe_pos, float)  # probe body origin in the last link's frame
     _, probe_c_local, probe_I = probe_geometry(p)
     Iprobe = Rh @ probe_I @ Rh.T
+    L = nj - 1
+    Il = np.array([[link[L, 16], link[L, 19], link[L, 20]], [link[L, 19], link[L, 17], link[L, 21]], [link[L, 20], link[L, 21], link[L, 18]]])
     parts = [
-        (p.link_mass[6], np.asarray(p.link_com[6], float), np.eye(3) * p.link_diaginertia[6]),
+        (p.link_mass[L], link[L, 12:15].copy(), Il),
         (p.hand_mass, ph, np.eye(3) * p.hand_diaginertia),
         (p.probe_mass, pp + Rh @ probe_c_local, Iprobe),
     ]
@@ -600,9 +648,9 @@ def _arm_tables(model: UltrasoundModel):
     for m, c, I in parts:
         d = c - ct
         It += I + m * (d @ d * np.eye(3) - np.outer(d, d))
-    link[6, 12:15] = ct
-    link[6, 15] = mt
-    link[6, 16:22] = [It[0, 0], It[1, 1], It[2, 2], It[0, 1], It[0, 2], It[1, 2]]
+    link[L, 12:15] = ct
+    link[L, 15] = mt
+    link[L, 16:22] = [It[0, 0], It[1, 1], It[2, 2], It[0, 1], It[0, 2], It[1, 2]]
     A["arm_link"] = link
 
     tool = np.zeros(34)

@@ -26,10 +26,13 @@ _ENV_KEYS = ("controller_configs", "control_freq", "horizon", "early_termination
 
 def env_from_config(cfg: dict, num_envs: int, seed: int, device, env_id_offset: int = 0) -> BatchedUltrasound:
     rs = dict(cfg["robosuite"])
-    assert rs.pop("env_id", "Ultrasound") == "Ultrasound" and rs.get("robots", "Panda") == "Panda"
+    assert rs.pop("env_id", "Ultrasound") == "Ultrasound" and rs.get("robots", "Panda") in ("Panda", "UR5e")
     if rs.get("use_camera_obs") or rs.get("has_renderer") or rs.get("has_offscreen_renderer"):
         raise NotImplementedError("rendering is out of scope of the hot path")
     extra = {} if rs.get("use_box_torso", True) else {"scene_params": cylinder_torso_params()}
+    if rs.get("robots", "Panda") == "UR5e":
+        from .model import ur5e_params
+        extra = {"scene_params": ur5e_params(extra.get("scene_params"))}
     return BatchedUltrasound(num_envs, device=device, seed=seed, env_id_offset=env_id_offset, **{k: rs[k] for k in _ENV_KEYS if k in rs}, **extra)
 
 
