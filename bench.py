@@ -244,6 +244,7 @@ def run_cuda(args):
     env.set_timing(False)
     diag = env.diag()
     mean_ncon, mean_iters = float(diag[:, 22].mean()), float(diag[:, 20].mean())
+    mean_rebuilds, mean_ls = float(diag[:, 24].mean()), float(diag[:, 25].mean())
 
     # ---------------- end to end through the host-buffer C-ABI call (H2D actions, D2H obs/reward/done inside)
     acts_h = [a.cpu().pin_memory().numpy() for a in acts]  # pinned host inputs, pinned host results (env.step_host)
@@ -304,6 +305,7 @@ def run_cuda(args):
                        "episode_phase": f"uniformly random per env + {preroll} untimed pre-roll steps (steady-state mix of resets and "
                                         "post-reset transients; independent of --steps/--warmup)",
                        "solver": f"PCG cap {args.iters}, relative gradient tolerance {args.tol or 3e-5:g}", "mean_ncon": mean_ncon, "mean_solver_iters": mean_iters,
+                       "mean_precond_rebuilds": mean_rebuilds, "mean_line_search_evals": mean_ls,
                        "l2": "state (~27 MB at 4096 envs) is smaller than L2; 256 MiB memset between steps, outside the per-step events"
                              if flush is not None else "not flushed"},
             "clocks": clocks,

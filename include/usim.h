@@ -199,8 +199,9 @@ int usim_get_contacts(usim_handle* h, int32_t* ncon_dev, int32_t* geom1_dev, int
 /* Per-env diagnostics of the last step, [num_envs][USIM_DIAG_DIM] float:
  * 0-2 cfrc_ext[probe][-3:] (ultrasound.py:365), 3-5 ee torque (:369),
  * 6-8 eef pos, 9-12 eef quat xyzw, 13-19 joint torques, 20 solver iterations,
- * 21 solver gradient norm, 22 ncon, 23 nefc */
-#define USIM_DIAG_DIM 24
+ * 21 solver gradient norm, 22 ncon (uncapped), 23 nefc, 24 preconditioner rebuilds, 25 line-search evaluations,
+ * 26-27 spare */
+#define USIM_DIAG_DIM 28
 int usim_get_diag(usim_handle* h, float* diag_dev, void* stream);
 
 /* Sizes the caller needs to allocate buffers. */

@@ -1353,6 +1353,7 @@ void oracle_diag(const oracle_env* e, double* d) {
   for (int k = 0; k < 4; k++) d[9 + k] = e->eef_quat[k];
   for (int k = 0; k < 7; k++) d[13 + k] = e->tau[k];
   d[20] = e->solver_iter; d[21] = e->solver_grad; d[22] = e->ncon; d[23] = e->nefc;
+  for (int k = 24; k < USIM_DIAG_DIM; k++) d[k] = 0;
 }
 void oracle_eef(const oracle_env* e, double* J, double* pos, double* mat) {
   if (J) memcpy(J, e->Jsite, sizeof e->Jsite);

@@ -16,7 +16,7 @@ USIM_ABI_VERSION = 2
 OBS_DIM = 19
 TASK_DIM = 48
 MAX_CONTACTS = 128
-DIAG_DIM = 24
+DIAG_DIM = 28
 
 GOAL_QUAT_XYZW = (-0.69192486, 0.72186726, -0.00514253, -0.01100909)  # ultrasound.py:174
 

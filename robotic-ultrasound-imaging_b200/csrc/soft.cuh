@@ -1114,7 +1114,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
 
   // ------------------------------------------------------------------ K6: nonlinear PCG; pass -1 evaluates the warm start
   float gpg = 1.f;
-  int iters = 0, rebuilds = 0;
+  int iters = 0, rebuilds = 0, ls_evals = 0;
   const int maxit = mode == 1 ? 2 * dm.iters : dm.iters;
   // every helper has exactly ONE call site (code size: the loop body must stay inside the instruction cache)
 #pragma unroll 1
@@ -1165,6 +1165,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
           d1 = rd(zl, 0) + q1 + alpha * q2;
           d2 = rd(zl, 1) + q2;
         }
+        ls_evals++;
         if (ls == 0) d0abs = fabsf(d1);
         if (fabsf(d1) <= LS_TOL * d0abs || !(d2 > 0.f)) break;
         if (d1 < 0.f) lo = alpha; else hi = alpha;
@@ -1407,6 +1408,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
       for (int j = 0; j < 7; j++) nlim += w.lsign[j] != 0.f;
       d[20] = (float)iters; d[21] = gnorm; d[22] = (float)ncon_found;
       d[23] = (float)(3 * ncon + nlim + (dm.soft ? 2 * 0 + np + dm.npair + 1 : 0));
+      d[24] = (float)rebuilds; d[25] = (float)ls_evals; d[26] = 0.f; d[27] = 0.f;
     }
   }
   // file the env for the next launch's order: by the iterations it took; a freshly reset env (cold start) goes first

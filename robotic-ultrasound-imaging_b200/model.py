@@ -195,16 +195,24 @@ class SceneParams:
     probe_pos: Tuple[float, float, float] = (-0.004, -0.063, 0.128)
     probe_mass: float = 1.0
     probe_friction: float = 1e-4
-    # radius calibrated against the reference's post-reset statistics [ART] (scripts/probe_sweep.py): in-contact fraction
-    # 0.79 (ART 0.78), max Fz 147 N (ART 174), median Fz 24 N (ART 34); r = 2 cm gave 0.73 / 51 / 12
-    probe_radius: float = 0.05
-    probe_tip_z: float = -0.05  # tip-sphere centre (tip surface at the grip_site origin)
+    # The reference's collision mesh is missing (A-PROBE-1): one capsule is substituted, CALIBRATED against the only reference-produced
+    # force / torque numbers there are -- the 192 raw post-reset observation rows of the shipped VecNormalize pickles
+    # (scripts/probe_calibrate.py, Nelder-Mead on 10 parameters over float64 oracle resets; profiles/r02_probe_fit2.json,
+    # profiles/r02_probe_calibration.md).  Result: a bar across the probe body's x axis (the wide, thin, rounded face of a convex-array
+    # probe, docs/images/press_torso_transparent.png), 5.8 cm between the end-sphere centres, radius 2.1 cm, lowest point 2 mm below the
+    # grip site, centre of mass 5 cm up the housing and ~8 mm off axis (from the F/T torque of the rows without contact).
+    # Round 1 shipped an axial capsule with a 5 cm tip sphere (probe_tip_z / probe_back_z below, still available by passing
+    # probe_seg_a = probe_seg_b = None): calibration loss 444 vs 40 for the bar; lateral force ratio 0.16 vs 0.29 (reference 0.38),
+    # z-torque spread 0.004 vs 0.18 N m (0.33), F/T torque without contact (0.075,-0.005,0) vs (0.083,-0.029,-0.006) ((0.091,-0.033,-0.007)).
+    probe_radius: float = 0.021
+    probe_tip_z: float = -0.05  # axial form: tip-sphere centre (with probe_radius 0.05: tip surface at the grip_site origin)
     probe_back_z: float = -0.10
-    # general form of the substituted capsule (probe-body frame, metres): segment end points and centre of mass; None = the
-    # axial capsule above ((0,0,probe_tip_z) .. (0,0,probe_back_z), COM at the middle of the segment)
-    probe_seg_a: Tuple[float, float, float] | None = None
-    probe_seg_b: Tuple[float, float, float] | None = None
-    probe_com: Tuple[float, float, float] | None = None
+    # general form of the substituted capsule (probe-body frame, metres; body +z points out of the probe face, i.e. down at the goal
+    # orientation): segment end points and centre of mass; None = the axial capsule ((0,0,probe_tip_z) .. (0,0,probe_back_z), COM at
+    # the middle of the segment)
+    probe_seg_a: Tuple[float, float, float] | None = (0.030, -0.0015, -0.019)
+    probe_seg_b: Tuple[float, float, float] | None = (-0.028, -0.0005, -0.019)
+    probe_com: Tuple[float, float, float] | None = (-0.006, -0.006, -0.052)
 
     # ---- soft composite (in tree): soft_box.xml (type box) or soft_human_torso.xml (type cylinder, `use_box_torso=False`)
     comp_type: str = "box"

@@ -421,6 +421,35 @@ def main():
     with open(os.path.join(OUT, "mjcf_golden.json"), "w") as f:
         json.dump({"soft_box": mjcf.read_assets(models, True), "soft_human_torso": mjcf.read_assets(models, False)}, f, indent=1)
     print("wrote mjcf_golden.json")
+    # utils/error.py (the consumer of the save_data CSV stream): run the reference's own calculate_error_metrics on a small synthetic
+    # episode and keep inputs + outputs (rui_b200/error_metrics.py must write the same files with the same numbers)
+    import tempfile
+    import pandas as pd
+    err = load(os.path.join(REF, "utils", "error.py"), "ref_error")
+    rng = np.random.default_rng(11)
+    H = 40
+    sim = {"ee_pos": rng.normal(size=(H, 3)), "ee_goal_pos": rng.normal(size=(H, 3)), "ee_vel": 0.05 * rng.normal(size=(H, 3)),
+           "ee_goal_vel": np.full(H, 0.04), "ee_running_mean_vel": 0.04 + 0.01 * rng.normal(size=H),
+           "ee_z_contact_force": 5 + 3 * rng.normal(size=H), "ee_z_goal_contact_force": np.full(H, 5.0),
+           "ee_z_running_mean_contact_force": 5 + rng.normal(size=H), "ee_z_derivative_contact_force": 100 * rng.normal(size=H),
+           "ee_z_goal_derivative_contact_force": np.zeros(H), "ee_diff_quat": np.abs(0.1 * rng.normal(size=H))}
+    rew = {k: rng.uniform(0, 3, size=H) for k in ("pos", "ori", "force", "derivative_force", "vel")}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.chdir(td)
+        try:
+            for fld, d in (("simulation_data", sim), ("reward_data", rew)):
+                os.makedirs(fld)
+                for k, v in d.items():
+                    pd.DataFrame(v).to_csv(os.path.join(fld, f"{k}_7.csv"), header=None, index=None)
+            err.calculate_error_metrics("7")
+            outs = {f[:-4]: open(os.path.join("error_data", "7", f)).read() for f in sorted(os.listdir(os.path.join("error_data", "7")))}
+        finally:
+            os.chdir(cwd)
+    with open(os.path.join(OUT, "error_metrics_golden.json"), "w") as f:
+        json.dump({"simulation_data": {k: jl(v) for k, v in sim.items()}, "reward_data": {k: jl(v) for k, v in rew.items()},
+                   "error_data_files": outs}, f, indent=1)
+    print("wrote error_metrics_golden.json:", sorted(outs))
 
 
 if __name__ == "__main__":

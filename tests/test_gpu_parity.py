@@ -714,3 +714,34 @@ def test_sb3_typed_vecenv_adapter(monkeypatch):
     q, v = ve.env_method("get_state", indices=3)[0]
     assert q.shape == (284,) and v.shape == (283,)
     ve.close()
+
+
+def test_ur5e_parity(O):
+    """robots="UR5e" (ultrasound.py:137): arm kernels compiled for 6 joints + the inert slot, against the oracle's generic tree."""
+    from rui_b200.model import ur5e_params
+    kw = dict(torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=3, scene_params=ur5e_params())
+    n = 8
+    env = _make(n, True, CC_TRACK, **kw)
+    env.reset()
+    q0 = env.get_state()[0]
+    assert float(q0[:, 6].abs().max()) == 0.0
+    orcs = make_oracles(O, env, CC_TRACK, **kw)
+    obs0 = env.obs.cpu().numpy()
+    for i in range(n):  # the reset itself (IK on the UR5e chain) agrees with the oracle's
+        e = O.OracleEnv(env.packed, abi.make_config(1, CC_TRACK, control_freq=500, **{k: v for k, v in kw.items() if k != "scene_params"}), i)
+        oo = e.reset()
+        np.testing.assert_allclose(q0[i, :7].cpu().numpy(), e.get_state()[0][:7], atol=5e-5)
+        np.testing.assert_allclose(obs0[i, 12:19], oo[12:19], atol=5e-5)
+    acts = np.random.default_rng(4).uniform(0, 1, size=(40, n, 6))
+    dr, log = compare_rollout(O, env, orcs, acts)
+    _assert_drift(dr, TOL_SOFT, "UR5e")
+    assert not log["done_mismatch"] and not log["contact_mismatch"]
+    assert float(env.get_state()[0][:, 6].abs().max()) == 0.0 and float(env.get_state()[1][:, 6].abs().max()) == 0.0
+    env.close()
+    # the robosuite-style single env accepts the robot name
+    from rui_b200.env import make
+    e1 = make("Ultrasound", robots="UR5e", controller_configs=CC_TRACK, control_freq=500, horizon=3, seed=3)
+    e1.reset()
+    od, r, d, _ = e1.step(np.full(6, 0.5))
+    assert e1.robots[0].name == "UR5e" and e1.robots[0].dof == 6 and e1.robots[0]._joint_positions.shape == (6,) and 0 <= r <= 12
+    e1.close()

@@ -13,18 +13,37 @@ pytestmark = pytest.mark.gpu
 
 
 def test_reference_policy_closed_loop_statistics():
+    """The reference's shipped `tracking` policy (+ its VecNormalize statistics) drives the env closed loop; every force / torque /
+    velocity channel of the observation statistics is held against the reference's 40 M-sample running statistics [ART], as ratios.
+
+    Not equalities, for reasons written out per channel in profiles/r02_probe_calibration.md: the reference numbers are a mixture
+    over the whole TRAINING run (early random policies included), the probe's collision mesh is missing (a calibrated capsule
+    stands in: smooth, no facet noise), and the arm constants are recalled.  The bounds are regression guards around what the
+    calibrated probe achieves (round 1's spherical tip: Fx variance ratio 0.006, z-torque variance ratio 0.0004, torque means 70x off)."""
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     from closed_loop_probe import run
     out = run(envs=1024, steps=1200)
-    # same order as the reference's 40 M-sample statistics (not equality: probe geometry / arm constants are assumptions)
-    assert 0.6 * out["art_step_reward"] <= out["step_reward"] <= 12.0
-    assert out["ep_len_mean"] >= 0.5 * out["art_ep_len_mean"]
-    assert abs(out["reset_in_contact_fraction"] - out["art_reset_in_contact_fraction"]) < 0.15
+    m, am = np.array(out["obs_mean"]), np.array(out["art_obs_mean"])
+    v, av = np.array(out["obs_var"]), np.array(out["art_obs_var"])
+    rm, rv = m / am, v / av
+    # episode-level behaviour (the artifacts' last 100 episodes: the FINAL policy)
+    assert 0.9 * out["art_step_reward"] <= out["step_reward"] <= 1.1 * out["art_step_reward"]      # measured 0.98
+    assert 0.75 * out["art_ep_len_mean"] <= out["ep_len_mean"] <= 1.35 * out["art_ep_len_mean"]     # measured 1.20-1.25
+    # reset statistics (pure physics, no policy): the calibration target
+    assert abs(out["reset_in_contact_fraction"] - out["art_reset_in_contact_fraction"]) < 0.12
+    assert 0.7 < out["reset_fz_median_in_contact"] / out["art_reset_fz_median_in_contact"] < 1.4   # measured 0.98 (round 1: 0.68)
     np.testing.assert_allclose(out["reset_pos_err_mean"], out["art_reset_pos_err_mean"], atol=1.5e-3)
     np.testing.assert_allclose(out["reset_pos_err_std"], out["art_reset_pos_err_std"], rtol=0.35)
-    m, am = np.array(out["obs_mean"]), np.array(out["art_obs_mean"])
-    assert m[2] > 1.0 and 0.2 < m[2] / am[2] < 5.0           # the policy keeps the probe pressed: mean Fz same order
-    assert abs(m[12] - am[12]) < 3e-3 and abs(m[13] - am[13]) < 3e-3 and abs(m[14] - am[14]) < 8e-3  # tracking error (m)
+    # contact force: Fz mean / variance, lateral components
+    assert 0.5 < rm[2] < 2.0 and 0.15 < rv[2] < 2.0            # measured 0.80 / 0.30
+    assert rm[0] > 0.08 and rv[0] > 0.05 and rv[1] > 0.015     # Fx has the reference's sign; lateral spread measured 0.11 / 0.03 (see report)
+    # F/T torque: y mean within a factor 2.5, every variance above a tenth of the reference's
+    assert 0.5 < rm[4] < 2.5 and (rv[3:6] > 0.1).all()         # measured mean 1.4; variances 0.22 / 0.39 / 0.21
+    # eef velocity, force statistics, velocity statistics
+    assert ((rv[6:9] > 0.5) & (rv[6:9] < 3.0)).all()           # measured 2.0 / 1.5 / 1.6
+    assert 0.2 < rv[9] < 2.0 and 0.5 < rv[10] < 2.5 and 0.5 < rv[11] < 3.0   # Fz mean 0.36, dFz 1.28, speed mean 1.62
+    # tracking error and orientation
+    assert abs(m[12] - am[12]) < 3e-3 and abs(m[13] - am[13]) < 3e-3 and abs(m[14] - am[14]) < 6e-3  # (m)
     assert m[15] < -0.5                                      # quaternion dot ~ -1 (A-QUAT-1)
     assert out["art_reset_pos_err_mean"][2] > 0.004          # the systematic +z reset offset exists in the artifacts
 

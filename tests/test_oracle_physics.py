@@ -10,6 +10,11 @@ from rui_b200 import abi
 from rui_b200.model import build_model, forward_kinematics, mass_matrix
 
 
+# the single-contact closed-form tests use the simplest probe shape: an axial capsule whose tip sphere touches the table in ONE point
+# exactly below the grip site (the shipped, calibrated probe is a bar with two end spheres: two table contacts)
+AXIAL_PROBE = dict(probe_seg_a=None, probe_seg_b=None, probe_com=None, probe_radius=0.05)
+
+
 def _cfg(cc, **kw):
     return abi.make_config(1, cc, control_freq=500, horizon=1000, **kw)
 
@@ -136,12 +141,12 @@ def test_single_soft_contact_closed_form(O):
     """Probe tip pressed into the rigid table at rest, arm locked by a huge gain: compare the contact force of the
     7-DoF solve with the closed-form 1-row answer f = -D (J a - aref) of the regularised constraint."""
     from rui_b200.model import SceneParams
-    pk = abi.PackedModel(build_model(SceneParams(soft_torso=False, table_friction=1e-6, probe_friction=1e-6)))  # frictionless
+    pk = abi.PackedModel(build_model(SceneParams(soft_torso=False, table_friction=1e-6, probe_friction=1e-6, **AXIAL_PROBE)))  # frictionless
     m = pk.model
     e = O.OracleEnv(pk, _cfg(CC_FIXED), 0)
     e.reset()
     # find a configuration with the probe tip 1 mm inside the table
-    e2 = O.OracleEnv(abi.PackedModel(build_model()), _cfg(CC_TRACK), 0)
+    e2 = O.OracleEnv(abi.PackedModel(build_model(SceneParams(**AXIAL_PROBE))), _cfg(CC_TRACK), 0)
     q = e2.ik([0.0, 0.0, 0.8 - 0.001])
     e.set_state(qpos=q, qvel=np.zeros(7))
     e.forward(np.zeros(7))
@@ -185,11 +190,11 @@ def test_friction_cone_solution_satisfies_the_optimality_conditions(O):
     solution satisfies M (a - a_smooth) = J^T f, and f is the cone force of J a - aref computed by an independent numpy
     restatement of the elliptic-cone formulas -- in all three zones; when sliding, |f_t| = friction * f_n exactly."""
     from rui_b200.model import SceneParams
-    pk = abi.PackedModel(build_model(SceneParams(soft_torso=False)))
+    pk = abi.PackedModel(build_model(SceneParams(soft_torso=False, **AXIAL_PROBE)))
     m = pk.model
     e = O.OracleEnv(pk, _cfg(CC_FIXED), 0)
     e.reset()
-    q = O.OracleEnv(abi.PackedModel(build_model()), _cfg(CC_TRACK), 0).ik([0.0, 0.0, 0.8 - 0.001])
+    q = O.OracleEnv(abi.PackedModel(build_model(SceneParams(**AXIAL_PROBE))), _cfg(CC_TRACK), 0).ik([0.0, 0.0, 0.8 - 0.001])
     e.set_state(qpos=q, qvel=np.zeros(7))
     e.forward(np.zeros(7))
     J0 = e.eef()[0]
@@ -487,3 +492,26 @@ def test_arm_links_stay_clear_of_torso_and_table(O, soft_model):
                     worst_torso = min(worst_torso, np.linalg.norm(d) - 0.08)
                     worst_table = min(worst_table, p[2] - 0.8 - 0.08)
     assert worst_torso > 0.05 and worst_table > 0.05, (worst_torso, worst_table)
+
+
+def test_ur5e_model_has_an_inert_seventh_arm_slot(O):
+    """robots="UR5e" (ultrasound.py:137,833-839): six joints; the seventh arm slot of the state is a rotor coupled to nothing, so
+    the 7-wide arm layout of the kernels is exact for a 6-joint arm.  The reset IK puts the probe on the trajectory point in the
+    goal orientation, and the slot never moves."""
+    from rui_b200.abi import PackedModel
+    from rui_b200.model import ur5e_params
+    pk = PackedModel(build_model(ur5e_params()))
+    assert pk.struct.narm == 6 and pk.model.nq == 284 and pk.model.nv == 283
+    e = O.OracleEnv(pk, _cfg(CC_TRACK, seed=3, torso_solref_randomization=True, initial_probe_pos_randomization=True, reset_eef_bias=(0, 0, 0)), 0)
+    obs = e.reset()
+    J, pos, mat = e.eef()
+    assert np.abs(J[:, 6]).max() == 0.0
+    assert np.linalg.norm(obs[12:14]) < 0.01 and abs(obs[14]) < 0.04 and obs[15] < -0.9999  # on the trajectory point (+ reset noise), goal orientation
+    M = e.M
+    assert abs(M[6, 6] - 1.0) < 1e-12 and np.abs(np.delete(M[6], 6)).max() == 0.0
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        e.step(rng.uniform(0, 1, 6))
+    q, v, _, _ = e.get_state()
+    assert q[6] == 0.0 and v[6] == 0.0
+    assert np.isfinite(q).all() and np.abs(v[:6]).max() < 5.0

@@ -199,3 +199,29 @@ def test_scene_params_match_the_reference_mjcf():
     assert "cap_radius" in mjcf.check_scene_params(dataclasses.replace(SceneParams(), cap_radius=0.008), gold["soft_box"])
     assert gold["soft_box"]["gripper"]["mesh_file"] == "meshes/ultrasound_probe_mesh.stl"  # (missing from the reference: A-PROBE-1)
     assert gold["soft_box"]["arena"]["colliding_geoms"] == ["floor", "table_collision"]
+
+
+def test_error_metrics_match_the_reference_files(tmp_path):
+    """SURVEY 8(f) rank 3, second half: `rui_b200.error_metrics.calculate_error_metrics` over the save_data CSV stream writes the
+    files `src/utils/error.py:calculate_error_metrics` writes (error_data/<model>/<metric>.csv) with the same numbers.  Golden:
+    the reference's own module executed on a synthetic episode (tests/golden/make_golden.py -> error_metrics_golden.json)."""
+    import json
+    import os
+
+    import pandas as pd
+
+    from rui_b200.error_metrics import calculate_error_metrics
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "error_metrics_golden.json")) as f:
+        g = json.load(f)
+    for fld in ("simulation_data", "reward_data"):
+        os.makedirs(tmp_path / fld)
+        for k, v in g[fld].items():
+            pd.DataFrame(np.array(v)).to_csv(tmp_path / fld / f"{k}_7.csv", header=None, index=None)
+    m = calculate_error_metrics("7", root=str(tmp_path))
+    files = sorted(os.listdir(tmp_path / "error_data" / "7"))
+    assert files == sorted(k + ".csv" for k in g["error_data_files"]) and len(files) == 13
+    for k, text in g["error_data_files"].items():
+        ref = float(text)
+        got = float(open(tmp_path / "error_data" / "7" / (k + ".csv")).read())
+        assert abs(got - ref) <= 1e-12 * max(1.0, abs(ref)), (k, got, ref)
+        assert abs(m[k] - ref) <= 1e-12 * max(1.0, abs(ref))
