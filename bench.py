@@ -48,17 +48,22 @@ def ncu_traffic(envs_per_gpu):
     return None if t is None else t["dram_bytes_per_launch"] * envs_per_gpu / t["envs_per_launch"]
 
 
-def issue_slots(envs_per_gpu, kernel_ms, sm_mhz, n_sm=148):
+def issue_slots(envs_per_gpu, kernel_ms, sm_mhz, mean_iters, n_sm=148):
     """The bound that actually applies: warp instructions issued per second against 4 schedulers x SMs x clock.
-    Instruction count per launch from the committed ncu capture (scaled to this launch's env count), time measured live."""
+    Instructions per launch = the committed ncu capture's count, scaled to this launch's env count and to the LIVE solver work:
+    the loop share of the instructions (80 %, profiles/r02_ncu_source_regions.txt) scales with the CG iterations per env-step
+    counted by the kernel in this very run (diag[20]); the time is measured live."""
     t = _ncu_capture()
     if t is None or "warp_instructions_per_launch" not in t or not sm_mhz:
         return None
-    inst = t["warp_instructions_per_launch"] * envs_per_gpu / t["envs_per_launch"]
+    loop = t.get("loop_share_of_instructions", 0.8)
+    it0 = t.get("mean_solver_iters_of_capture") or mean_iters
+    inst = t["warp_instructions_per_launch"] * envs_per_gpu / t["envs_per_launch"] * ((1 - loop) + loop * mean_iters / it0)
     achieved = inst / (kernel_ms * 1e-3) / 1e9
     peak = 4 * n_sm * sm_mhz * 1e6 / 1e9
     return {"bound": "fp32 issue slots (secondary, informative)", "achieved": achieved, "peak": peak, "unit": "G warp-instr/s",
-            "frac": achieved / peak, "source": "smsp__inst_executed.sum of profiles/r01_ncu_summary.md x live kernel time"}
+            "frac": achieved / peak, "live_mean_cg_iterations": mean_iters,
+            "source": "smsp__inst_executed.sum of the committed capture (profiles/traffic.json) scaled by the live CG iteration count, over the live kernel time"}
 
 
 def peaks():
@@ -154,6 +159,12 @@ def run_reference(args):
         tot += n
     dt = time.perf_counter() - t0
     val = tot / dt
+    # BASELINE config 1 literally: ONE env on one host core (the shape the reference's Ultrasound env has inside each SubprocVecEnv worker)
+    one = envs[:1]
+    a1 = rng.uniform(0, 1, size=(max(40, int(3.0 * rate0 / threads)), 1, 6))
+    t1 = time.perf_counter()
+    n1, _ = O.rollout(one, a1, auto_reset=True, threads=1)
+    single = n1 / (time.perf_counter() - t1)
     line = {
         "impl": "reference", "metric": "ultrasound env-steps/sec", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
@@ -163,7 +174,10 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
                          "sample": f"{threads} envs x {per_step} steps per bench step, 3 forward passes per step as in the reference"},
         "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "restated-reference CPU baseline (mujoco-py unavailable); artifact-derived historical figure: 385.5 env-steps/s on 64 workers",
+        "config1_single_env": {"value": single, "unit": "env-steps/s", "cores": 1, "sample": f"1 env x {a1.shape[0]} steps",
+                               "note": "BASELINE config 1: single env, OSC_POSE, random actions, one host core"},
+        "note": "restated-reference CPU baseline (mujoco-py unavailable): a float64 port of the published algorithms, NOT mujoco-py; "
+                "artifact-derived historical figure of the reference itself: 385.5 env-steps/s on 64 workers (6 per worker, PPO updates and hard resets included)",
     }
     print(json.dumps(line), flush=True)
 
@@ -306,12 +320,14 @@ def run_cuda(args):
                                         "post-reset transients; independent of --steps/--warmup)",
                        "solver": f"PCG cap {args.iters}, relative gradient tolerance {args.tol or 3e-5:g}", "mean_ncon": mean_ncon, "mean_solver_iters": mean_iters,
                        "mean_precond_rebuilds": mean_rebuilds, "mean_line_search_evals": mean_ls,
-                       "l2": "state (~27 MB at 4096 envs) is smaller than L2; 256 MiB memset between steps, outside the per-step events"
+                       "l2": "state (~37 MB at 4096 envs) is smaller than L2; 256 MiB memset between steps, outside the per-step events"
                              if flush is not None else "not flushed"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": per_gpu * env.action_dim * 4,
                     "d2h_bytes_per_step": per_gpu * (19 * 4 + 4 + 1),
-                    "note": "obs + reward + done every step; terminal observations only for the envs that finished in the step"},
+                    "note": "obs + reward + done every step; terminal observations only for the envs that finished in the step; "
+                            "early_termination off as in the device-resident line (with it on, as rl_config.yaml:53 trains, a few envs "
+                            "finish in every step and their terminal rows are fetched one by one: --early-termination)"},
             "gpu_launches": int(launches),
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -320,7 +336,7 @@ def run_cuda(args):
         }
         if strong_ref is not None:
             line["strong_ref"] = strong_ref
-        iss = issue_slots(per_gpu, kernel_ms, clocks.get("sm_mhz"))
+        iss = issue_slots(per_gpu, kernel_ms, clocks.get("sm_mhz"), mean_iters)
         if iss is not None:
             line["issue_slots"] = iss
         if world == 1 and not args.no_cpu:

@@ -1,9 +1,8 @@
 #!/bin/bash
-# usage: bash scripts/multi_gpu_round.sh <N> <tag> [ppo]   -- bench.py on N GPUs of one box (torchrun, NCCL), optionally the PPO driver
-N=$1; tag=$2
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 100 --warmup 10 > gpurun_out/bench_${tag}_n$N.json 2> gpurun_out/bench_${tag}_n$N.err
-tail -c 400 gpurun_out/bench_${tag}_n$N.json
-if [ "$3" = "ppo" ]; then
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 -m rui_b200.rl --config examples/rl_config_smoke.yaml --num-envs 65536 --n-steps 32 --total-timesteps 4.2e7 > gpurun_out/ppo_${tag}_n$N.log 2>&1
-  tail -4 gpurun_out/ppo_${tag}_n$N.log
-fi
+# usage: bash scripts/multi_gpu_round.sh <N> <tag>   (under gpurun --gpus N): config 4 scaling line (+ strong_ref) and config 5 PPO line
+N=${1:-2}; tag=${2:-r02}
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/bench_${tag}_n$N.json 2> gpurun_out/bench_${tag}_n$N.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --workload ppo --steps 5 --warmup 3 > gpurun_out/bench_${tag}_ppo_n$N.json 2> gpurun_out/bench_${tag}_ppo_n$N.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus $N --steps 2 --warmup 1 > gpurun_out/bench_${tag}_ref_n$N.json 2> gpurun_out/bench_${tag}_ref_n$N.err
+for f in gpurun_out/bench_${tag}_n$N.json gpurun_out/bench_${tag}_ppo_n$N.json gpurun_out/bench_${tag}_ref_n$N.json; do echo "== $f"; tail -1 $f | cut -c1-1800; done
+tail -3 gpurun_out/bench_${tag}_n$N.err gpurun_out/bench_${tag}_ppo_n$N.err | cut -c1-300
