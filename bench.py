@@ -304,6 +304,13 @@ def run_cuda(args):
             big.close()
         barrier()
 
+    # BASELINE config 5 in the same run (all ranks: the gradient all-reduce is an NCCL collective), so that the PPO figure is in the
+    # driver's record too; a few seconds
+    ppo = None
+    if not args.no_ppo:
+        env.close()  # (idempotent; rank 0 may have closed it for the strong_ref measurement)
+        ppo = measure_ppo(args, world, rank, local, args.ppo_iters, 3)
+
     if rank == 0:
         peak, which = peaks()
         achieved = per_gpu * ALG_BYTES_PER_ENV_STEP / (kernel_ms * 1e-3) / 1e9
@@ -336,6 +343,8 @@ def run_cuda(args):
         }
         if strong_ref is not None:
             line["strong_ref"] = strong_ref
+        if ppo is not None:
+            line["ppo"] = {k: v for k, v in ppo.items() if k != "clocks"}
         iss = issue_slots(per_gpu, kernel_ms, clocks.get("sm_mhz"), mean_iters)
         if iss is not None:
             line["issue_slots"] = iss
@@ -353,24 +362,18 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
-def run_ppo(args):
-    """--workload ppo: BASELINE config 5 -- PPO training from rl_config.yaml hyper-parameters on GPU-batched rollouts, one process
-    per GPU, envs sharded over the ranks, gradients averaged by one flat NCCL all-reduce per minibatch.  One bench "step" = one PPO
-    iteration = a rollout of n_steps control steps of every env + n_epochs x minibatches optimiser steps."""
+def measure_ppo(args, world, rank, local, steps, warmup):
+    """BASELINE config 5 -- PPO training from rl_config.yaml hyper-parameters on GPU-batched rollouts, one process per GPU, envs
+    sharded over the ranks, gradients averaged by one flat NCCL all-reduce per minibatch.  One "step" here = one PPO iteration = a
+    rollout of n_steps control steps of every env + n_epochs x minibatches optimiser steps.  Returns the result dict on rank 0."""
     import torch
     import torch.distributed as dist
 
     from rui_b200.env import BatchedUltrasound
     from rui_b200.ppo import PPO
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    per_gpu = args.envs or 8192  # config 5 at 8 GPUs: 65536 envs
+    per_gpu = args.ppo_envs  # config 5 at 8 GPUs: 65536 envs
     opts = dict(ENV_OPTS, early_termination=True)  # rl_config.yaml:53
     env = BatchedUltrasound(per_gpu, device=dev, seed=SEED, env_id_offset=rank * per_gpu, **opts)
     n_steps = args.n_steps
@@ -384,50 +387,77 @@ def run_ppo(args):
         torch.cuda.synchronize()
 
     model._setup()
-    for _ in range(max(args.warmup, 3)):  # includes the CUDA-graph capture of the minibatch step
+    for _ in range(max(warmup, 3)):  # includes the CUDA-graph capture of the minibatch step
         model.train(model.collect_rollouts())
     model.allreduce_ms()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = env.launch_count
-    e0, e1, em = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), []
+    e0, e1, er = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), []
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
         batch = model.collect_rollouts()
-        m = torch.cuda.Event(enable_timing=True)
-        m.record()
-        em.append(m)
+        b.record()
+        er.append((a, b))
         model.train(batch)
     e1.record()
     barrier()
     clocks = sampler.result()
     ms = e0.elapsed_time(e1)
+    rollout_ms = sum(a.elapsed_time(b) for a, b in er)
     ar_ms, ar_n = model.allreduce_ms()
-    t = torch.tensor([ms, ar_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, ar_ms, rollout_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, ar_max = [float(x) for x in t.tolist()]
-    total = per_gpu * world * n_steps * args.steps
+    ms_max, ar_max, ro_max = [float(x) for x in t.tolist()]
+    total = per_gpu * world * n_steps * steps
+    launches = int(env.launch_count - l0)
+    stats = dict(model.last_stats)
+    nmb = (per_gpu * n_steps) // model.batch_size
+    res = {
+        "value": total / (ms_max * 1e-3), "unit": "env-steps/s", "n_gpus": world, "iterations": steps, "ms_per_iteration": ms_max / steps,
+        "rollout_ms_per_iteration": ro_max / steps, "update_ms_per_iteration": (ms_max - ro_max) / steps,
+        "allreduce_ms_per_iteration": ar_max / steps, "allreduces_per_iteration": ar_n / max(steps, 1),
+        "allreduce_bytes": 4 * sum(p.numel() for p in model.policy.parameters()),
+        "config": {"workload": f"BASELINE config 5: PPO training (rl_config.yaml hyper-parameters) on {per_gpu * world} GPU-batched envs, "
+                               f"{world} GPU(s), NCCL gradient all-reduce",
+                   "envs_total": per_gpu * world, "envs_per_gpu": per_gpu, "n_steps": n_steps,
+                   "n_steps_note": "the reference's 2048 x 64 envs; 2048 x 65536 would exceed total_timesteps (SURVEY 8d cfg 5)",
+                   "n_epochs": model.n_epochs, "minibatches_per_epoch": nmb, "batch_size_per_gpu": model.batch_size,
+                   "iteration": "rollout (n_steps control steps of every env) + update", "early_termination": True,
+                   "policy": "MlpPolicy pi/vf [256,128] (76,941 parameters), random init"},
+        "step_reward_mean": stats.get("step_reward_mean"), "ep_len_mean": stats.get("ep_len_mean"), "gpu_launches": launches, "clocks": clocks,
+    }
+    env.close()
+    return res
+
+
+def run_ppo(args):
+    """--workload ppo: the config-5 measurement as the line's own value."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    args.ppo_envs = args.envs or args.ppo_envs
+    r = measure_ppo(args, world, rank, local, args.steps, args.warmup)
     if rank == 0:
-        nmb = (per_gpu * n_steps) // model.batch_size
         line = {
-            "metric": "ultrasound env-steps/sec", "value": total / (ms_max * 1e-3), "unit": "env-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "metric": "ultrasound env-steps/sec", "value": r["value"], "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_iteration"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BASELINE config 5: PPO training (rl_config.yaml hyper-parameters) on {per_gpu * world} GPU-batched envs, "
-                                   f"{world} GPU(s), NCCL gradient all-reduce",
-                       "envs_total": per_gpu * world, "envs_per_gpu": per_gpu, "n_steps": n_steps,
-                       "n_steps_note": "the reference's 2048 x 64 envs; 2048 x 65536 would exceed total_timesteps (SURVEY 8d cfg 5)",
-                       "n_epochs": model.n_epochs, "minibatches_per_epoch": nmb, "batch_size_per_gpu": model.batch_size,
-                       "bench_step": "one PPO iteration: rollout (n_steps control steps of every env) + update",
-                       "early_termination": True, "policy": "MlpPolicy pi/vf [256,128] (76,941 parameters), random init",
-                       "l2": "rollout buffers (19 obs x n_steps x envs) exceed nothing relevant; not flushed"},
-            "clocks": clocks, "gpu_launches": int(env.launch_count - l0),
-            "ppo": {"allreduce_ms_per_iteration": ar_max / args.steps, "allreduces_per_iteration": ar_n / max(args.steps, 1),
-                    "allreduce_bytes": 4 * sum(p.numel() for p in model.policy.parameters()),
-                    "step_reward_mean": model.last_stats.get("step_reward_mean"), "ep_len_mean": model.last_stats.get("ep_len_mean")},
-            "e2e": {"value": total / (ms_max * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+            "config": dict(r["config"], bench_step="one PPO iteration", l2="not flushed (the update streams ~100 MB of rollout buffers per epoch)"),
+            "clocks": r["clocks"], "gpu_launches": r["gpu_launches"],
+            "ppo": {k: r[k] for k in ("rollout_ms_per_iteration", "update_ms_per_iteration", "allreduce_ms_per_iteration",
+                                      "allreduces_per_iteration", "allreduce_bytes", "step_reward_mean", "ep_len_mean")},
+            "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "note": "training keeps observations, actions and rewards on the device: there is no host hop in this workload"},
         }
         print(json.dumps(line), flush=True)
@@ -442,7 +472,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="env", choices=["env", "ppo"], help="env: the env step (configs 3/4, default); ppo: config 5")
-    ap.add_argument("--n-steps", type=int, default=32, help="--workload ppo: rollout length per PPO iteration")
+    ap.add_argument("--n-steps", type=int, default=32, help="PPO: rollout length per iteration")
+    ap.add_argument("--ppo-envs", type=int, default=8192, help="PPO: envs per GPU (config 5: 65536 over 8 GPUs)")
+    ap.add_argument("--ppo-iters", type=int, default=3, help="PPO iterations timed at the end of the default run (config 5 sub-record)")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the config-5 PPO sub-measurement of the default run")
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: BASELINE configs)")
     ap.add_argument("--iters", type=int, default=40, help="solver iteration cap")
     ap.add_argument("--rebuilds", type=int, default=0, help="preconditioner rebuilds allowed per solve (0: library default)")

@@ -8,6 +8,17 @@
 
 // NJ = number of real arm joints: 7 (Panda) or 6 (UR5e).  Every per-env array keeps 7 slots; with NJ = 6 the seventh is an inert,
 // decoupled degree of freedom (unit inertia, no Jacobian column, no torque), so the solve kernel and the state layout do not change.
+// The per-link loops of the arm kernel can be ROLLED (ARM_ROLL=1): the kernel runs one thread per env, one warp per SM, and is
+// bound by instruction fetch (fully unrolled: ~5 500 straight-line instructions executed once at ~8 cycles each); rolled, the loop bodies
+// are fetched once and reused, at the price of link arrays in local memory (L1 resident).
+#ifndef ARM_ROLL
+#define ARM_ROLL 0 // measured at 4096 envs: rolled 3184 instead of ~5500 SASS instructions, arm launch 2 us shorter (29.4 vs 31.5 us step minus solve kernel), the step as a whole unchanged (0.528 ms): not kept
+#endif
+#if ARM_ROLL
+#define ARM_LOOP _Pragma("unroll 1")
+#else
+#define ARM_LOOP _Pragma("unroll")
+#endif
 struct ArmKin {
   float R[7][9];  // link frames
   v3 p[7];        // link origins == joint anchors
@@ -20,7 +31,7 @@ template <int NJ>
 __device__ __forceinline__ void arm_fk(const float* q, ArmKin& k) {
   float Rp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   v3 pp = mk(0, 0, 0);
-#pragma unroll
+ARM_LOOP
   for (int j = 0; j < NJ; j++) {
     k.p[j] = pp + mv(Rp, ld3(dm.link_pos[j]));
     float T[9], Rz[9];
@@ -108,7 +119,7 @@ __device__ __forceinline__ void arm_forward(int mode, bool policy_step, const fl
   v3 w[7], al[7], ac[7]; // angular vel, angular acc (vp), linear acc of the link origin (vp, with -g)
   {
     v3 wp = mk(0, 0, 0), alp = mk(0, 0, 0), acp = mk(-dm.g[0], -dm.g[1], -dm.g[2]), pp = mk(0, 0, 0);
-#pragma unroll
+ARM_LOOP
     for (int j = 0; j < NJ; j++) {
       v3 r = k.p[j] - pp;
       v3 zq = qd[j] * k.z[j];
@@ -128,7 +139,7 @@ __device__ __forceinline__ void arm_forward(int mode, bool policy_step, const fl
     v3 F = mk(0, 0, 0), N = mk(0, 0, 0); // accumulated force / moment about p[j+1]
     v3 pn = k.p[NJ - 1];
     float cm = 0.f; v3 cc = mk(0, 0, 0); float Ic[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}; // composite mass, com, inertia about com
-#pragma unroll
+ARM_LOOP
     for (int j = NJ - 1; j >= 0; j--) {
       v3 cl = mv(k.R[j], ld3(dm.link_com[j]));
       v3 com = k.p[j] + cl;
@@ -216,7 +227,7 @@ __device__ __forceinline__ void arm_forward(int mode, bool policy_step, const fl
     for (int i = 0; i < 49; i++) L[i] = M[i];
     chol<7>(L);
     float MiJt[42]; // [7][6]
-#pragma unroll
+ARM_LOOP
     for (int r = 0; r < 6; r++) {
       float col[7];
 #pragma unroll
@@ -308,7 +319,7 @@ __device__ __forceinline__ void arm_forward(int mode, bool policy_step, const fl
     v3 acom = ac[LL] + cross(al[LL], cl) + cross(w[LL], cross(w[LL], cl));
     v3 t0 = mv(Iw, al[LL]) + cross(w[LL], mv(Iw, w[LL])) + cross(rc, mp * acom);
     tau0[0] = t0.x; tau0[1] = t0.y; tau0[2] = t0.z;
-#pragma unroll
+ARM_LOOP
     for (int j = 0; j < 7; j++) {
       if (j < NJ) {
         v3 jr = k.z[j];

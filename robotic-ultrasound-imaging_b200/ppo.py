@@ -185,7 +185,9 @@ class PPO:
         torch.manual_seed(seed + 1000 * (self.rank + 1))
         # On a CUDA device one minibatch step is replayed as two CUDA graphs (launch bound otherwise: ~100 small kernels per step)
         self.cuda_graph = (self.device.type == "cuda") if cuda_graph is None else bool(cuda_graph)
-        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5, capturable=self.cuda_graph)
+        # fused multi-tensor Adam on CUDA: one kernel for the 12 parameter tensors instead of ~10 foreach kernels per step
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5, capturable=self.cuda_graph,
+                                    fused=(self.device.type == "cuda"))
         self._graphs = None
         self.norm = VecNormalizeState(self.N, self.obs_dim, self.device, gamma=gamma) if normalize else None
         lo, hi = env.action_spec
@@ -306,32 +308,35 @@ class PPO:
         saved_s = {p: {k: v.clone() for k, v in st.items() if torch.is_tensor(v)} for p, st in self.opt.state.items()}
         stats = [torch.zeros((), device=dev) for _ in range(3)]
 
+        # every p.grad is a VIEW into one flat buffer: backward accumulates into it in place, the NCCL all-reduce works on the
+        # buffer itself, clipping is one norm + one scale of the buffer -- no concatenation, no copies back
+        flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
+        off = 0
+        for p in params:
+            k = p.numel()
+            p.grad = flat_grad[off:off + k].view_as(p)
+            off += k
+
         def part_a():
+            flat_grad.zero_()
             loss, pl, vl, kl = self._minibatch_loss(bufs[0][idx], bufs[1][idx], bufs[2][idx], bufs[3][idx], bufs[4][idx])
             loss.backward()
             for t, v in zip(stats, (pl, vl, kl)):
                 t.copy_(v.detach())
-            return torch.cat([p.grad.reshape(-1) for p in params])
+            return flat_grad
 
         def part_b(flat):
             if self.world > 1:
-                flat = flat / self.world
-            off = 0
-            for p in params:
-                k = p.numel()
-                p.grad.copy_(flat[off:off + k].view_as(p))
-                off += k
-            nn.utils.clip_grad_norm_(params, self.max_grad_norm, foreach=True)
+                flat.div_(self.world)
+            flat.mul_(torch.clamp(self.max_grad_norm / (flat.norm() + 1e-6), max=1.0))  # clip_grad_norm_ on the flat buffer
             self.opt.step()
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(3):
-                self.opt.zero_grad(set_to_none=True)
                 part_b(part_a())
         torch.cuda.current_stream(dev).wait_stream(side)
-        self.opt.zero_grad(set_to_none=True)
         ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(ga):
             flat = part_a()
