@@ -196,9 +196,13 @@ def test_bench_roofline_helpers_read_the_committed_capture():
     assert bench.ncu_traffic(4096) == pytest.approx(t["dram_bytes_per_launch"]) and bench.ncu_traffic(8192) == pytest.approx(2 * t["dram_bytes_per_launch"])
     # traffic at or below the algorithmic bytes: the state stays in L2 between steps, nothing is re-read from HBM
     assert t["dram_bytes_per_launch"] <= 4096 * bench.ALG_BYTES_PER_ENV_STEP
-    iss = bench.issue_slots(4096, 0.43, 1965.0)
+    iss = bench.issue_slots(4096, 0.50, 1965.0, t["mean_solver_iters_of_capture"])
     assert iss["unit"] == "G warp-instr/s" and 0.2 < iss["frac"] < 1.0 and iss["peak"] == pytest.approx(4 * 148 * 1.965)
-    assert bench.issue_slots(4096, 0.43, None) is None
+    assert iss["achieved"] == pytest.approx(t["warp_instructions_per_launch"] / 0.50e-3 / 1e9)  # same iteration count as the capture: unscaled
+    # the loop share of the instructions scales with the LIVE iteration count the kernel reports
+    more = bench.issue_slots(4096, 0.50, 1965.0, 2 * t["mean_solver_iters_of_capture"])
+    assert more["achieved"] == pytest.approx(iss["achieved"] * (1 + t["loop_share_of_instructions"]))
+    assert bench.issue_slots(4096, 0.43, None, 5.0) is None
 
 
 def test_committed_bench_lines_follow_the_contract():
@@ -206,7 +210,8 @@ def test_committed_bench_lines_follow_the_contract():
     import json
     need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
             "data", "config", "clocks", "e2e", "gpu_launches", "roofline"}
-    for name, n in (("r01_bench.json", 1), ("r01_bench_2gpu.json", 2), ("r01_bench_4gpu.json", 4), ("r01_bench_8gpu.json", 8)):
+    for name, n in (("r01_bench.json", 1), ("r01_bench_2gpu.json", 2), ("r01_bench_4gpu.json", 4), ("r01_bench_8gpu.json", 8),
+                    ("r02_bench.json", 1), ("r02_bench_2gpu.json", 2), ("r02_bench_driver_style.json", 1)):
         d = json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
         assert need <= set(d), need - set(d)
         assert d["n_gpus"] == n and d["unit"] == "env-steps/s" and d["higher_is_better"] is True and d["dtype"] == "f32"
