@@ -745,3 +745,45 @@ def test_ur5e_parity(O):
     od, r, d, _ = e1.step(np.full(6, 0.5))
     assert e1.robots[0].name == "UR5e" and e1.robots[0].dof == 6 and e1.robots[0]._joint_positions.shape == (6,) and 0 <= r <= 12
     e1.close()
+
+
+@pytest.mark.parametrize("horizon", [1, 2, 7])
+def test_reset_pipeline_matches_oracle_resets_under_back_to_back_terminations(O, horizon):
+    """The reset states are prepared ahead of time on a side stream, two slots per env, and taken over inside the step kernel.  Worst
+    case for that protocol: every env terminates every `horizon` steps (horizon 1: a slot is consumed EVERY step, so the slot freed at
+    step t must be refilled before step t + 2).  After every termination the live state / observation equal the oracle's reset for
+    that (env, episode number), the terminal observation is the step's own, and episode counters advance by exactly one."""
+    from rui_b200.env import packed_model
+    kw = dict(torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=9, horizon=horizon)
+    n, steps = 48, 12
+    env = _make(n, True, CC_TRACK, **kw)
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    okw = {k: v for k, v in kw.items()}
+    oracles = [O.OracleEnv(packed_model(True), abi.make_config(1, CC_TRACK, control_freq=500, **okw), i) for i in range(6)]
+    for s in range(1, steps + 1):
+        o, r, d, tobs = env.step(torch.rand(n, 6, device="cuda", generator=gen), auto_reset=True)
+        q, v, w, t = _np(*env.get_state())
+        o, tobs = _np(o, tobs)
+        if s % horizon:
+            assert not bool(d.any())
+            continue
+        assert bool(d.all())
+        ep = 1 + s // horizon
+        assert (t[:, abi.TS_EPISODE] == ep).all() and (t[:, abi.TS_TIMESTEP] == 0).all() and (t[:, abi.TS_DONE] == 0).all()
+        assert np.all(v == 0) and np.all(w == 0)
+        assert not np.array_equal(tobs, o)
+        for i, e in enumerate(oracles):  # the oracle's reset number `ep` of env i (episode key ep - 1)
+            ts0 = np.zeros(abi.TASK_DIM)
+            ts0[abi.TS_EPISODE] = ep - 1
+            e.set_state(task=ts0)
+            oo = e.reset()
+            oq, _, _, ot = e.get_state()
+            np.testing.assert_allclose(q[i, :7], oq[:7], atol=3e-5)
+            np.testing.assert_allclose(q[i, 7:], oq[7:], atol=1e-6)
+            assert t[i, abi.TS_STIFFNESS] == ot[abi.TS_STIFFNESS] and t[i, abi.TS_DAMPING] == ot[abi.TS_DAMPING]
+            np.testing.assert_allclose(t[i, :7], ot[:7], atol=2e-7)
+            np.testing.assert_allclose(o[i, 12:19], oo[12:19], atol=3e-5)
+            np.testing.assert_allclose(o[i, :3], oo[:3], rtol=3e-2, atol=0.3)
+            assert o[i, 10] == 0 and o[i, 11] == pytest.approx(-0.04)
+    env.close()
