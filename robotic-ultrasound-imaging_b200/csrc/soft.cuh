@@ -416,6 +416,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
   for (int i = tid; i < 49; i += NT) w.Sf[i] = (i % 8 == 0) ? 1.f : 0.f; // identity: row/col 6 of the padded 6x6 stay like this
   mbar_wait(&w.bar, phase);
   phase ^= 1;
+  if (!qv_g) env_sync(); // the zero rows above were written by plain stores of other threads (racecheck), not by the bulk copies the wait orders
   for (int i = nv + tid; i < QPAD; i += NT) w.x[i] = 0.f; // the solver vectors are zero beyond nv
   if (tid < 7) {
     w.qdarm[tid] = w.hs[tid];
