@@ -204,6 +204,15 @@ int usim_get_contacts(usim_handle* h, int32_t* ncon_dev, int32_t* geom1_dev, int
 #define USIM_DIAG_DIM 28
 int usim_get_diag(usim_handle* h, float* diag_dev, void* stream);
 
+/* Arm record of the last physics step, [num_envs][USIM_ARM_RECORD_DIM] float: what robosuite's controller reads through
+ * mujoco-py every substep (osc.py update(): `sim.data.qM` / `cymj._mj_fullM`, `get_site_jacp/jacr`, site pose) plus the
+ * controller output.  0-48 joint-space inertia M (7x7 row major), 49-55 qfrc_smooth of the arm, 56-62 clipped joint torques,
+ * 63-104 grip-site Jacobian (rows 0-2 linear, 3-5 angular; 6x7), 105-125 hand-body linear Jacobian (3x7), 126-128 site position,
+ * 129-137 site orientation (row major), 138-143 probe capsule end points, 144-146 / 147-167 F/T torque sensor: bias part and
+ * linear map from the arm accelerations (3x7), 168-171 eef quaternion xyzw, 172-178 warm-start shift of the solver. */
+#define USIM_ARM_RECORD_DIM 180
+int usim_get_arm_record(usim_handle* h, float* rec_dev, void* stream);
+
 /* Sizes the caller needs to allocate buffers. */
 int usim_num_envs(const usim_handle* h);
 int usim_nq(const usim_handle* h);

@@ -17,6 +17,7 @@ OBS_DIM = 19
 TASK_DIM = 48
 MAX_CONTACTS = 128
 DIAG_DIM = 28
+ARM_RECORD_DIM = 180  # usim_get_arm_record row pitch (usim.h)
 
 GOAL_QUAT_XYZW = (-0.69192486, 0.72186726, -0.00514253, -0.01100909)  # ultrasound.py:174
 

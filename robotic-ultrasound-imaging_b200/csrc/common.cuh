@@ -153,6 +153,25 @@ __device__ __forceinline__ void chol_solve(const float* L, float* x) {
   }
 }
 
+// x <- (L L^T)^-1 x for the leading N x N block of a factor written by chol7_warp2 / chol7_group: lower triangle, diagonal INVERTED (row pitch 7)
+template <int N>
+__device__ __forceinline__ void chol7_solve(const float* L, float* x) {
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    float t = x[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) t -= L[i * 7 + k] * x[k];
+    x[i] = t * L[i * 7 + i];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) {
+    float t = x[i];
+#pragma unroll
+    for (int k = i + 1; k < N; k++) t -= L[k * 7 + i] * x[k];
+    x[i] = t * L[i * 7 + i];
+  }
+}
+
 // ---------------------------------------------------------------- Philox4x32-10 (bit-exact with the oracle)
 __device__ __forceinline__ void philox(unsigned k0, unsigned k1, unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned* out) {
 #pragma unroll

@@ -31,6 +31,7 @@
 #define MINB (WPE <= 2 ? 8 : 16 / WPE) // resident CTAs per SM the register allocation is sized for
 #endif
 #define NPAIR_MAX 544
+#define SLOT_OBS 20 // row pitch of a prepared observation (19 used)
 // Slider block of the preconditioner, D - W (D: diagonal, W: the pair couplings of the shell grid), inverted by a polynomial in
 // N = D^-1 W.  PREC3 = 0: second order, D^-1 (I + N).  PREC3 = 1: third order with Chebyshev weights, D^-1 (I + c (N + N^2)),
 // c = 4 / (4 - 3 rho^2): the cubic (1 - x) p(x) = 1 - T3(x / rho) / T3(1 / rho) deviates least from 1 on the spectrum [-rho, rho]
@@ -104,8 +105,11 @@ struct __align__(16) WS {
   int ncon, okf;
   int consume;                                         // this env's episode ended and a prepared reset slot takes over (K9 -> all threads)
   int cnt[2][WPE];                                     // cross-warp prefix of the contact compaction (double buffered)
+  float orow[SLOT_OBS];                                // observation row of this step (K9, thread 0) -> written out as ONE coalesced row
 };
+#ifndef SKIP_SMEM_ASSERT
 static_assert(sizeof(WS) + 1024 <= 233472 / MINB, "WS must leave room for MINB CTAs per SM");
+#endif
 static_assert(2 * QPAD >= NPAIR_MAX + 1, "pg|s double as the pair scratch of K3");
 
 __device__ __forceinline__ void env_sync() {
@@ -269,25 +273,6 @@ __device__ __forceinline__ bool chol7_warp2(float* A0, float* A1, int lane) {
     if (act && k <= r) A[r * 7 + k] = row[k];
   return ok;
 }
-// x <- (L L^T)^-1 x for the leading N x N block of a factor written by chol7_warp2 (row pitch 7)
-template <int N>
-__device__ __forceinline__ void chol7_solve(const float* L, float* x) {
-#pragma unroll
-  for (int i = 0; i < N; i++) {
-    float t = x[i];
-#pragma unroll
-    for (int k = 0; k < i; k++) t -= L[i * 7 + k] * x[k];
-    x[i] = t * L[i * 7 + i];
-  }
-#pragma unroll
-  for (int i = N - 1; i >= 0; i--) {
-    float t = x[i];
-#pragma unroll
-    for (int k = i + 1; k < N; k++) t -= L[k * 7 + i] * x[k];
-    x[i] = t * L[i * 7 + i];
-  }
-}
-
 // x <- (L L^T)^-1 b for TWO factors written by chol7_warp2, at once, by one warp: lane r (0..6) holds entry r of the right-hand side of
 // A0, lane 8 + r that of A1; the solution entry comes back in the same lane.  Column-oriented substitution: one broadcast shuffle and
 // one FMA per column (28 shuffles in all) instead of the ~290 replicated, fully unrolled instructions of chol7_solve<7> + <6> in every
@@ -322,7 +307,6 @@ __device__ __forceinline__ float chol7_solve_warp2(const float* A0, const float*
 // takes env order[j].  The block scheduler hands CTAs out in index order, so the slow envs start first and the tail of the launch
 // (3.5 waves at 4096 envs) is made of the quick ones.  Which CTA runs an env never changes its result.
 #define NBIN 16
-#define SLOT_OBS 20 // row pitch of a prepared observation (19 used)
 
 // Reset pipeline.  The state an env is reset to is a pure function of (seed, global env id, episode number): it is PREPARED ahead of
 // time, off the critical path, into one of two per-env slots (slot k holds an episode number with parity k), by the reset kernel +
@@ -1387,8 +1371,9 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
     // auto-reset (SB3 VecEnv semantics): the env takes over its prepared slot below; this step's observation is the terminal one
     const bool consume = mode == 0 && a.auto_reset && dn;
     w.consume = consume;
-    float* o = consume ? (a.tobs ? a.tobs + (size_t)env * USIM_OBS_DIM : nullptr) : obs_row;
-    if (o) { // ultrasound.py:363-401
+    { // ultrasound.py:363-401; staged in shared memory, stored by 19 lanes below (one coalesced row: the destination may be
+      // page-locked HOST memory, usim_step_host)
+      float* o = w.orow;
       o[0] = cfrc.x; o[1] = cfrc.y; o[2] = cfrc.z; o[3] = ft.x; o[4] = ft.y; o[5] = ft.z; o[6] = hv.x; o[7] = hv.y; o[8] = hv.z;
       o[9] = o_fz; o[10] = o_dfz; o[11] = o_vel;
       o[12] = eef.x - o_tp.x; o[13] = eef.y - o_tp.y; o[14] = eef.z - o_tp.z;
@@ -1418,6 +1403,10 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
     a.bin_items[(size_t)b * n + atomicAdd(a.bin_cnt + b, 1)] = env;
   }
   env_sync();
+  if (mode != 2 && tid < USIM_OBS_DIM) { // this step's observation: the terminal one if a prepared reset state takes over below
+    float* o = w.consume ? (a.tobs ? a.tobs + (size_t)env * USIM_OBS_DIM : nullptr) : obs_row;
+    if (o) o[tid] = w.orow[tid];
+  }
   if (w.consume) {
     // The episode is over and auto-reset is on: the prepared slot (episode number E = the live record's counter, slot E & 1) becomes
     // the live state.  Velocity and warm start of a reset state are zero.  Then ask for episode E + 2 to be prepared in this slot.

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "arm.cuh"
+#include "arm_warp.cuh"
 #include "common.cuh"
 #include "soft.cuh"
 
@@ -61,7 +62,7 @@ struct usim_handle {
   bool ev_prep_valid[2] = {false, false};
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_state = nullptr; // recorded on the caller's stream after every state-mutating call: usim_step_host waits on it
-  bool ev_state_valid = false, timing = false;
+  bool ev_state_valid = false, timing = false, arm_thread = false, host_copy = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
   int64_t launches = 0, timed_launches = 0;
   double timed_ms = 0.0;
@@ -277,6 +278,8 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
     CKH(cudaEventCreateWithFlags(&h->ev_prep[0], cudaEventDisableTiming));
     CKH(cudaEventCreateWithFlags(&h->ev_prep[1], cudaEventDisableTiming));
   }
+  if (const char* at = getenv("USIM_ARM_THREAD")) h->arm_thread = atoi(at) != 0;
+  if (const char* hc = getenv("USIM_HOST_COPY")) h->host_copy = atoi(hc) != 0;
   h->smem = sizeof(WS);
   if (const char* pad = getenv("USIM_SMEM_PAD")) h->smem += (size_t)atoi(pad); // developer knob: trade resident CTAs for L1 capacity
   CKH(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
@@ -329,10 +332,18 @@ static int mark_state(usim_handle* h, cudaStream_t s) {
 }
 
 // the arm / reset kernels are compiled per joint count (arm.cuh NJ)
-#define ARM_LAUNCH(h, grid, block, stream, ...)                                                   \
-  do {                                                                                            \
-    if ((h)->narm == 7) arm_kernel<7><<<grid, block, 0, stream>>>(__VA_ARGS__);                   \
-    else arm_kernel<6><<<grid, block, 0, stream>>>(__VA_ARGS__);                                  \
+// (arm_thread: developer knob USIM_ARM_THREAD=1, the thread-per-env kernel of round 1 -- kept for A/B measurements and as a second opinion)
+#define ARM_LAUNCH(h, stream, ...)                                                                                        \
+  do {                                                                                                                    \
+    const int n_ = (h)->n;                                                                                                \
+    if ((h)->arm_thread) {                                                                                                \
+      if ((h)->narm == 7) arm_kernel<7><<<(n_ + ARM_BLOCK - 1) / ARM_BLOCK, ARM_BLOCK, 0, stream>>>(__VA_ARGS__);         \
+      else arm_kernel<6><<<(n_ + ARM_BLOCK - 1) / ARM_BLOCK, ARM_BLOCK, 0, stream>>>(__VA_ARGS__);                        \
+    } else {                                                                                                              \
+      const int epb_ = ARMW_BLOCK / GW;                                                                                   \
+      if ((h)->narm == 7) arm_kernel_w<7><<<(n_ + epb_ - 1) / epb_, ARMW_BLOCK, 0, stream>>>(__VA_ARGS__);                \
+      else arm_kernel_w<6><<<(n_ + epb_ - 1) / epb_, ARMW_BLOCK, 0, stream>>>(__VA_ARGS__);                               \
+    }                                                                                                                     \
   } while (0)
 #define RESET_LAUNCH(h, grid, block, stream, ...)                                                 \
   do {                                                                                            \
@@ -390,7 +401,7 @@ static int launch_step(usim_handle* h, const float* act, float* obs, float* rew,
   for (int sub = 0; sub < nsub; sub++) {
     const bool last = sub == nsub - 1;
     const int b = (int)(h->solve_tick & 1); // this launch files into bins b; its order comes from bins 1 - b
-    ARM_LAUNCH(h, (n + ARM_BLOCK - 1) / ARM_BLOCK, ARM_BLOCK, s, n, h->qpos, h->qvel, act, h->task, h->armbuf, sub == 0 ? done : nullptr,
+    ARM_LAUNCH(h, s, n, h->qpos, h->qvel, act, h->task, h->armbuf, sub == 0 ? done : nullptr,
                sub == 0, NBIN, h->bin_cnt + (1 - b) * NBIN, h->bin_items + (size_t)(1 - b) * NBIN * n, h->bin_cnt + b * NBIN, h->order);
     SolveArgs a = base_args(h, last ? 0 : 2);
     a.obs = obs; a.rew = rew; a.done = done; a.tobs = tobs;
@@ -463,36 +474,61 @@ static bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+// device-side alias of a page-locked host buffer (UVA: cudaHostAlloc / cudaHostRegister / torch pin_memory are mapped), or nullptr
+static void* mapped_alias(const void* p) {
+  void* d = nullptr;
+  if (!p || !is_pinned(p)) return nullptr;
+  if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return d;
+}
+
 int usim_step_host(usim_handle* h, const float* act, float* obs, float* rew, uint8_t* done, float* tobs, int auto_reset) {
   if (!h) return fail("usim_step_host: null handle");
   if (!act) return fail("usim_step_host: act is required");
   if (activate(h)) return -1;
   cudaStream_t s = h->own_stream;
   size_t N = (size_t)h->n;
+  const size_t row = USIM_OBS_DIM * sizeof(float);
   // Caller buffers that are page-locked are used directly; pageable ones go through the library's pinned staging buffers.
   const float* a_src = act;
   if (!is_pinned(act)) { memcpy(h->h_act, act, N * h->adim * sizeof(float)); a_src = h->h_act; }
-  float* o_dst = obs && is_pinned(obs) ? obs : h->h_obs;
   float* r_dst = rew && is_pinned(rew) ? rew : h->h_rew;
   uint8_t* d_dst = done && is_pinned(done) ? done : h->h_done;
-  float* t_dst = tobs && is_pinned(tobs) ? tobs : h->h_tobs;
+  // Observation rows -- and the terminal rows of the envs that finish in this step, typically ~N / episode length of them -- are
+  // written by the solve kernel STRAIGHT into page-locked host memory (one coalesced 76-byte row per env, posted PCIe writes that
+  // overlap the rest of the launch): no device->host copy of the 19-column array after the kernel, no second round trip for the
+  // terminal rows, and only the rows of finished envs are touched in `term_obs_host`.  (USIM_HOST_COPY=1: the copy-based path.)
+  float* o_host = obs && is_pinned(obs) ? obs : h->h_obs;
+  float* t_host = tobs && is_pinned(tobs) ? tobs : h->h_tobs;
+  float* o_dev = h->host_copy ? nullptr : (float*)mapped_alias(o_host);
+  float* t_dev = h->host_copy ? nullptr : (float*)mapped_alias(t_host);
+  float* r_dev = h->host_copy ? nullptr : (float*)mapped_alias(r_dst);     // reward and done flag of an env: two more posted writes
+  uint8_t* d_dev = h->host_copy ? nullptr : (uint8_t*)mapped_alias(d_dst);
+  const bool zero_copy = o_dev && t_dev && r_dev && d_dev;
   // the private stream is ordered after the last state-mutating call made on a caller's stream (usim_reset / usim_step /
   // usim_set_state), and this call synchronises it before returning: the two kinds of call may be mixed freely
   if (h->ev_state_valid) CK(cudaStreamWaitEvent(s, h->ev_state, 0));
   CK(cudaMemcpyAsync(h->d_act, a_src, N * h->adim * sizeof(float), cudaMemcpyHostToDevice, s));
-  if (usim_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, tobs ? h->d_tobs : nullptr, auto_reset, s)) return -1;
-  CK(cudaMemcpyAsync(o_dst, h->d_obs, N * USIM_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(r_dst, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(d_dst, h->d_done, N, cudaMemcpyDeviceToHost, s));
+  if (zero_copy) {
+    if (usim_step(h, h->d_act, o_dev, r_dev, d_dev, tobs ? t_dev : nullptr, auto_reset, s)) return -1;
+  } else {
+    if (usim_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, tobs ? h->d_tobs : nullptr, auto_reset, s)) return -1;
+    CK(cudaMemcpyAsync(o_host, h->d_obs, N * row, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(r_dst, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(d_dst, h->d_done, N, cudaMemcpyDeviceToHost, s));
+  }
   CK(cudaStreamSynchronize(s));
-  if (obs && o_dst != obs) memcpy(obs, h->h_obs, N * USIM_OBS_DIM * sizeof(float));
+  if (obs && o_host != obs) memcpy(obs, o_host, N * row);
   if (rew && r_dst != rew) memcpy(rew, h->h_rew, N * sizeof(float));
   if (done && d_dst != done) memcpy(done, h->h_done, N);
-  if (tobs) {
-    // Terminal observations exist only for the envs that finished in this step (typically ~N / episode length of them): fetch those
-    // rows alone; when many envs finish together (a common horizon) one copy of the whole array into the library's staging buffer
-    // is cheaper.  Either way ONLY the rows of finished envs are written into the caller's array.
-    const size_t row = USIM_OBS_DIM * sizeof(float);
+  if (tobs && zero_copy) {
+    if (t_host != tobs) { // pageable caller array: the kernel wrote the finished envs' rows into the staging buffer
+      for (size_t e = 0; e < N; e++)
+        if (d_dst[e]) memcpy(tobs + e * USIM_OBS_DIM, t_host + e * USIM_OBS_DIM, row);
+    }
+  } else if (tobs) {
+    // copy-based path: fetch the rows of the finished envs alone; when many envs finish together (a common horizon) one copy of
+    // the whole array into the library's staging buffer is cheaper.  Either way ONLY the rows of finished envs are written.
     size_t ndone = 0;
     for (size_t e = 0; e < N; e++) ndone += d_dst[e] != 0;
     if (ndone > 64) {
@@ -502,9 +538,9 @@ int usim_step_host(usim_handle* h, const float* act, float* obs, float* rew, uin
         if (d_dst[e]) memcpy(tobs + e * USIM_OBS_DIM, h->h_tobs + e * USIM_OBS_DIM, row);
     } else if (ndone > 0) {
       for (size_t e = 0; e < N; e++)
-        if (d_dst[e]) CK(cudaMemcpyAsync(t_dst + e * USIM_OBS_DIM, h->d_tobs + e * USIM_OBS_DIM, row, cudaMemcpyDeviceToHost, s));
+        if (d_dst[e]) CK(cudaMemcpyAsync(t_host + e * USIM_OBS_DIM, h->d_tobs + e * USIM_OBS_DIM, row, cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
-      if (t_dst != tobs) {
+      if (t_host != tobs) {
         for (size_t e = 0; e < N; e++)
           if (d_dst[e]) memcpy(tobs + e * USIM_OBS_DIM, h->h_tobs + e * USIM_OBS_DIM, row);
       }
@@ -547,6 +583,13 @@ int usim_set_state(usim_handle* h, const float* qpos, const float* qvel, const f
   if (task) rc(h, USIM_TASK_DIM, USIM_TASK_DIM, USIM_TASK_DIM, task, h->task, s);
   CK(cudaGetLastError());
   return mark_state(h, s);
+}
+
+int usim_get_arm_record(usim_handle* h, float* rec, void* stream) {
+  if (!h || !rec) return fail("usim_get_arm_record: null argument");
+  static_assert(USIM_ARM_RECORD_DIM == ARMBUF, "the ABI's arm-record pitch is the kernels' row pitch");
+  CK(cudaMemcpyAsync(rec, h->armbuf, (size_t)h->n * ARMBUF * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
 }
 
 int usim_get_contacts(usim_handle* h, int32_t* ncon, int32_t* g1, int32_t* g2, float* dist, void* stream) {

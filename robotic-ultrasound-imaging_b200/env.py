@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .abi import (DIAG_DIM, MAX_CONTACTS, OBS_DIM, TASK_DIM, PackedModel, action_bounds, action_dim, make_config)
+from .abi import (ARM_RECORD_DIM, DIAG_DIM, MAX_CONTACTS, OBS_DIM, TASK_DIM, PackedModel, action_bounds, action_dim, make_config)
 from .model import SceneParams, UltrasoundModel, build_model, cylinder_torso_params
 
 SENSOR_NAMES = (  # ultrasound.py:394-401, dims App. A.4
@@ -197,6 +197,13 @@ class BatchedUltrasound:
         d = torch.empty(self.num_envs, DIAG_DIM, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().usim_get_diag(self._h, _ptr(d), self._stream()))
+        return d
+
+    def arm_record(self):
+        """[N][180] arm record of the last physics step (M, qfrc_smooth, torques, Jacobians, site pose ...: usim.h)."""
+        d = torch.empty(self.num_envs, ARM_RECORD_DIM, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().usim_get_arm_record(self._h, _ptr(d), self._stream()))
         return d
 
     @property

@@ -787,3 +787,62 @@ def test_reset_pipeline_matches_oracle_resets_under_back_to_back_terminations(O,
             np.testing.assert_allclose(o[i, :3], oo[:3], rtol=3e-2, atol=0.3)
             assert o[i, 10] == 0 and o[i, 11] == pytest.approx(-0.04)
     env.close()
+
+
+def test_arm_record_matches_oracle(O):
+    """K1/K2 pinned directly: the arm record of every step (joint-space inertia, qfrc_smooth, clipped torques, site Jacobian and
+    pose: what robosuite's controller reads through mujoco-py) against the oracle's generic tree formulation.  Tolerances = 4x the
+    maxima measured on a B200 (fp32 lane-per-link kernel vs float64); the state is re-synchronised every step so that the
+    comparison is of ONE forward pass on identical inputs."""
+    kw = dict(torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=3)
+    n = 8
+    env = _make(n, True, CC_TRACK, **kw)
+    env.reset()
+    orcs = make_oracles(O, env, CC_TRACK, **kw)
+    acts = np.random.default_rng(7).uniform(0, 1, size=(12, n, 6))
+    worst = dict(M=0.0, qs=0.0, tau=0.0, J=0.0, pos=0.0, R=0.0)
+    for s in range(12):
+        q, v, w, t = _np(*env.get_state())
+        for i, e in enumerate(orcs):
+            e.set_state(q[i], v[i], w[i], t[i])
+            e.step(acts[s, i])
+        env.step(torch.as_tensor(acts[s], dtype=torch.float32, device="cuda"))
+        rec = env.arm_record().cpu().numpy().astype(np.float64)
+        for i, e in enumerate(orcs):
+            J, pos, mat = e.eef()
+            qs = e.tau - e.bias[:7] - env.model.g_dof_damping[:7] * v[i, :7]
+            worst["M"] = max(worst["M"], np.abs(rec[i, 0:49].reshape(7, 7) - e.M[:7, :7]).max())
+            worst["qs"] = max(worst["qs"], np.abs(rec[i, 49:56] - qs).max())
+            worst["tau"] = max(worst["tau"], np.abs(rec[i, 56:63] - e.tau).max())
+            worst["J"] = max(worst["J"], np.abs(rec[i, 63:105].reshape(6, 7) - J).max())
+            worst["pos"] = max(worst["pos"], np.abs(rec[i, 126:129] - pos).max())
+            worst["R"] = max(worst["R"], np.abs(rec[i, 129:138].reshape(3, 3) - mat).max())
+    tol = dict(M=2e-5, qs=1e-2, tau=1e-2, J=4e-6, pos=4e-6, R=4e-6)
+    bad = {k: (worst[k], tol[k]) for k in tol if not worst[k] <= tol[k]}
+    assert not bad, (bad, worst)
+    env.close()
+
+
+def test_lane_per_link_arm_kernel_agrees_with_the_thread_per_env_kernel(monkeypatch):
+    """Two independent implementations of K1/K2 on the device: serial chain walk by one thread (round 1, USIM_ARM_THREAD=1) and
+    scans over 8 lanes (default).  Same inputs -> every field of the arm record agrees to fp32 rounding; a 30-step rollout stays
+    within the drift of two fp32 evaluation orders."""
+    recs = {}
+    for thread in (1, 0):
+        monkeypatch.setenv("USIM_ARM_THREAD", str(thread))
+        env = _make(64, True, CC_TRACK, torso_solref_randomization=True, initial_probe_pos_randomization=True, seed=5)
+        env.reset()
+        gen = torch.Generator(device="cpu").manual_seed(1)
+        acts = torch.rand(30, 64, 6, generator=gen).cuda()
+        env.step(acts[0])
+        rec1 = env.arm_record().clone()
+        for s in range(1, 30):
+            env.step(acts[s])
+        recs[thread] = (rec1, env.get_state()[0].clone(), env.get_state()[1].clone())
+        env.close()
+    a, b = recs[1][0], recs[0][0]
+    scale = {"M": (0, 49, 1e-5), "qs": (49, 56, 4e-3), "tau": (56, 63, 4e-3), "J": (63, 126, 2e-6), "pose": (126, 144, 2e-6),
+             "ft": (144, 168, 1e-5), "quat": (168, 172, 2e-6)}
+    for k, (i0, i1, tol) in scale.items():
+        assert float((a[:, i0:i1] - b[:, i0:i1]).abs().max()) <= tol, k
+    assert float((recs[1][1] - recs[0][1]).abs().max()) < 5e-5 and float((recs[1][2] - recs[0][2]).abs().max()) < 2e-3

@@ -33,6 +33,7 @@ def test_struct_mirrors_match_compiled_layout():
     assert int(re.search(r"#define USIM_MAX_CONTACTS (\d+)", hdr).group(1)) == abi.MAX_CONTACTS
     assert int(re.search(r"#define USIM_OBS_DIM (\d+)", hdr).group(1)) == abi.OBS_DIM
     assert int(re.search(r"#define USIM_DIAG_DIM (\d+)", hdr).group(1)) == abi.DIAG_DIM
+    assert int(re.search(r"#define USIM_ARM_RECORD_DIM (\d+)", hdr).group(1)) == abi.ARM_RECORD_DIM
     for name, val in re.findall(r"(USIM_TS_[A-Z_]+) = (\d+)", hdr):
         py = name.replace("USIM_", "")
         if hasattr(abi, py):
