@@ -30,6 +30,11 @@
 #ifndef MINB
 #define MINB (WPE <= 2 ? 8 : 16 / WPE) // resident CTAs per SM the register allocation is sized for
 #endif
+// More resident envs per SM do not pay (measured, 32 768 envs, round 2): with the preconditioner-only arrays in bfloat16, one-byte
+// contact slots and aliased reduction zones the env image shrinks to 24.3 KB = 9 CTAs per SM, but the 9th needs <= 112 registers:
+// 120 regs / 8 CTAs 8.83 M env-steps/s, 112 / 9: 8.47 M, 96 / 9: 8.34 M, 96 / 8: 8.00 M -- the register-capped schedule costs 5-9 %, the
+// extra CTA returns 4 %.  Three or four warps per env at 8 envs per SM (24 / 32 warps, 80 / 72 registers): 7.22 / 6.22 M against 7.82 M.
+// Fewer resident envs (USIM_SMEM_PAD): 7 / 6 / 5 CTAs per SM = 8.18 / 7.70 / 7.22 M.
 #define NPAIR_MAX 544
 #define SLOT_OBS 20 // row pitch of a prepared observation (19 used)
 // Slider block of the preconditioner, D - W (D: diagonal, W: the pair couplings of the shell grid), inverted by a polynomial in
@@ -741,7 +746,8 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
       if (sub_aref) rel = rel - mk(w.cjv[0][c], w.cjv[1][c], w.cjv[2][c]);
       out[0][c] = rel.x; out[1][c] = rel.y; out[2][c] = rel.z;
     }
-    env_sync();
+    // (no barrier: every per-contact loop of the solve maps contact c to the same thread, which is the only reader of out[.][c]
+    // until the next one)
   };
   // sum of a per-contact quantity over the contacts of slider i, called by its owner slot c: the second table contact sits in
   // the next slot, the probe contact (if any, and if it is not the owner itself) in cslot2
@@ -1120,7 +1126,8 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
         w.Hx[i] = hx; w.grad[i] = hx;
         rhs2 += r * r; hx2 += hx * hx;
       }
-      env_sync();
+      // (no barrier here: the first pass of update_grad touches per-contact data of this thread only; its own barrier comes before
+      // anybody reads the grad rows written above)
     } else {
       // ---- exact line search: Newton on phi'(alpha)
       float q1 = 0.f, q2 = 0.f, alpha = 0.f, lo = 0.f, hi = -1.f, d0abs = 0.f;
@@ -1170,7 +1177,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
       for (int c = tid; c < ncon; c += NT) {
         w.cjar[0][c] += alpha * w.cjv[0][c]; w.cjar[1][c] += alpha * w.cjv[1][c]; w.cjar[2][c] += alpha * w.cjv[2][c];
       }
-      env_sync();
+      // (no barrier, as above)
     }
     update_grad(hx2, rhs2);
     const bool changed = rd(w.rg, 12) > 0.f;
