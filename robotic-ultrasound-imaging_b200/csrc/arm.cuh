@@ -361,8 +361,9 @@ __global__ void __launch_bounds__(64) arm_kernel(int n, const float* __restrict_
                                                  const float* __restrict__ act, float* __restrict__ task, float* __restrict__ armbuf,
                                                  uint8_t* __restrict__ done, int policy_step, int nbin, const int* __restrict__ bin_cnt_prev,
                                                  const int* __restrict__ bin_items_prev, int* __restrict__ bin_cnt_next,
-                                                 int* __restrict__ order) {
+                                                 int* __restrict__ order, int* __restrict__ queue) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (queue && env == 0) *queue = 0; // work queue of the solve launch that follows
   if (env >= n) return;
   if (order) {
     int off = 0, b = nbin - 1;

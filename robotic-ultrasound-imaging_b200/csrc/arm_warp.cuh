@@ -374,7 +374,8 @@ __global__ void __launch_bounds__(ARMW_BLOCK) arm_kernel_w(int n, const float* _
                                                           const float* __restrict__ act, float* __restrict__ task, float* __restrict__ armbuf,
                                                           uint8_t* __restrict__ done, int policy_step, int nbin,
                                                           const int* __restrict__ bin_cnt_prev, const int* __restrict__ bin_items_prev,
-                                                          int* __restrict__ bin_cnt_next, int* __restrict__ order) {
+                                                          int* __restrict__ bin_cnt_next, int* __restrict__ order, int* __restrict__ queue) {
+  if (queue && blockIdx.x == 0 && threadIdx.x == 0) *queue = 0; // work queue of the solve launch that follows
   __shared__ __align__(16) float sm[ARMW_BLOCK / GW][ARMBUF + ARM_SCR];
   const int g = threadIdx.x / GW, j = threadIdx.x % GW;
   const int env = blockIdx.x * (ARMW_BLOCK / GW) + g;

@@ -109,6 +109,7 @@ struct __align__(16) WS {
   float Dt, areft;
   int ncon, okf;
   int consume;                                         // this env's episode ended and a prepared reset slot takes over (K9 -> all threads)
+  int item;                                            // work item fetched from the launch's queue (thread 0 -> all threads)
   int cnt[2][WPE];                                     // cross-warp prefix of the contact compaction (double buffered)
   float orow[SLOT_OBS];                                // observation row of this step (K9, thread 0) -> written out as ONE coalesced row
 };
@@ -341,6 +342,7 @@ struct SolveArgs {
   float *slot_qpos, *slot_task, *slot_obs; // [2][n][QPAD | USIM_TASK_DIM | SLOT_OBS]
   int *req_list, *req_cnt;         // (env, episode number) pairs to prepare, appended by this launch
   const int *prep_items, *prep_n;  // prepare mode: the requests this launch works through
+  int* queue;                      // persistent launch (grid = resident CTAs): next launch slot, fetched with atomicAdd (nullptr: item = blockIdx.x + k gridDim.x)
 };
 
 __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
@@ -359,7 +361,13 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
   const int nitems = a.prep ? *a.prep_n : n;
   // one trip per CTA for the env step (grid = n); the prepare launch walks its request list with a small fixed grid
 #pragma unroll 1
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+  for (int item = blockIdx.x;; item += gridDim.x) {
+  if (a.queue) { // dynamic hand-out in launch order (longest solves first): a CTA that finishes early takes the next slot
+    if (tid == 0) w.item = atomicAdd(a.queue, 1);
+    env_sync();
+    item = w.item;
+  }
+  if (item >= nitems) break;
   int env = item;
   float *qp_g, *qv_g, *wm_g, *ts_g, *obs_row;
   const float* ab_g;

@@ -51,6 +51,8 @@ struct usim_handle {
   uint8_t* d_resetmask = nullptr;
   // launch order of the solve kernel (longest solve first): bins filled by launch T, flattened by the arm kernel of launch T + 1
   int *bin_cnt = nullptr, *bin_items = nullptr, *order = nullptr; // [2][NBIN], [2][NBIN][n], [n]
+  int* queue = nullptr;  // work queue of a persistent step launch (next launch slot)
+  int step_grid = 0;     // CTAs of a step launch: every resident slot of the device once (0: one CTA per env)
   int64_t solve_tick = 0;
   // reset pipeline: two prepared reset states per env (slot k holds an episode number of parity k), made on a side stream
   float *slot_qpos = nullptr, *slot_task = nullptr, *slot_obs = nullptr, *prep_armbuf = nullptr;
@@ -254,6 +256,8 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
     CKH(cudaMalloc((void**)&h->bin_cnt, 2 * NBIN * sizeof(int)));
     CKH(cudaMalloc((void**)&h->bin_items, 2 * (size_t)NBIN * N * sizeof(int)));
     CKH(cudaMalloc((void**)&h->order, N * sizeof(int)));
+    CKH(cudaMalloc((void**)&h->queue, sizeof(int)));
+    CKH(cudaMemset(h->queue, 0, sizeof(int)));
     std::vector<int> cnt(2 * NBIN, 0), ident(N);
     cnt[NBIN] = (int)N;
     for (size_t e = 0; e < N; e++) ident[e] = (int)e;
@@ -281,6 +285,11 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   if (const char* at = getenv("USIM_ARM_THREAD")) h->arm_thread = atoi(at) != 0;
   if (const char* hc = getenv("USIM_HOST_COPY")) h->host_copy = atoi(hc) != 0;
   h->smem = sizeof(WS);
+  if (const char* pg = getenv("USIM_PERSISTENT")) { // developer knob: persistent step launch, one CTA per resident slot
+    int per_sm = 0;
+    if (atoi(pg) != 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel, NT, sizeof(WS)) == cudaSuccess && per_sm > 0)
+      h->step_grid = std::min(h->n, per_sm * prop.multiProcessorCount);
+  }
   if (const char* pad = getenv("USIM_SMEM_PAD")) h->smem += (size_t)atoi(pad); // developer knob: trade resident CTAs for L1 capacity
   CKH(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   CKH(cudaDeviceSynchronize());
@@ -296,7 +305,7 @@ int usim_destroy(usim_handle* h) {
   for (auto& p : h->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   void* dev[] = {h->counters, h->qpos, h->qvel, h->warm, h->task, h->armbuf, h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->ax4,
                  h->ps4, h->nb4, h->eq_pairs, h->d_act, h->d_obs, h->d_tobs, h->d_rew,
-                 h->d_done, h->d_resetmask, h->bin_cnt, h->bin_items, h->order, h->slot_qpos, h->slot_task, h->slot_obs, h->prep_armbuf,
+                 h->d_done, h->d_resetmask, h->bin_cnt, h->bin_items, h->order, h->queue, h->slot_qpos, h->slot_task, h->slot_obs, h->prep_armbuf,
                  h->req_list, h->req_cnt};
   for (void* p : dev) if (p) cudaFree(p);
   void* host[] = {h->h_act, h->h_obs, h->h_tobs, h->h_rew, h->h_done};
@@ -402,10 +411,12 @@ static int launch_step(usim_handle* h, const float* act, float* obs, float* rew,
     const bool last = sub == nsub - 1;
     const int b = (int)(h->solve_tick & 1); // this launch files into bins b; its order comes from bins 1 - b
     ARM_LAUNCH(h, s, n, h->qpos, h->qvel, act, h->task, h->armbuf, sub == 0 ? done : nullptr,
-               sub == 0, NBIN, h->bin_cnt + (1 - b) * NBIN, h->bin_items + (size_t)(1 - b) * NBIN * n, h->bin_cnt + b * NBIN, h->order);
+               sub == 0, NBIN, h->bin_cnt + (1 - b) * NBIN, h->bin_items + (size_t)(1 - b) * NBIN * n, h->bin_cnt + b * NBIN, h->order,
+               h->step_grid ? h->queue : nullptr);
     SolveArgs a = base_args(h, last ? 0 : 2);
     a.obs = obs; a.rew = rew; a.done = done; a.tobs = tobs;
     a.order = h->order; a.bin_cnt = h->bin_cnt + b * NBIN; a.bin_items = h->bin_items + (size_t)b * NBIN * n;
+    a.queue = h->step_grid ? h->queue : nullptr;
     if (last && auto_reset) {
       if (producer_begin(h, s)) return -1;
       a.auto_reset = 1;
@@ -417,7 +428,7 @@ static int launch_step(usim_handle* h, const float* act, float* obs, float* rew,
       CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
       CK(cudaEventRecord(e0, s));
     }
-    solve_kernel<<<n, NT, h->smem, s>>>(a);
+    solve_kernel<<<h->step_grid ? h->step_grid : n, NT, h->smem, s>>>(a);
     if (timed) {
       CK(cudaEventRecord(e1, s));
       h->pending.emplace_back(e0, e1);

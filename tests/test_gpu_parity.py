@@ -846,3 +846,41 @@ def test_lane_per_link_arm_kernel_agrees_with_the_thread_per_env_kernel(monkeypa
     for k, (i0, i1, tol) in scale.items():
         assert float((a[:, i0:i1] - b[:, i0:i1]).abs().max()) <= tol, k
     assert float((recs[1][1] - recs[0][1]).abs().max()) < 5e-5 and float((recs[1][2] - recs[0][2]).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("uncouple", [True, False])
+def test_osc_torques_towards_a_kinematic_singularity(O, uncouple):
+    """Lambda = pinv(J M^-1 J^T) in robosuite; the device takes a Cholesky inverse in fp32, the oracle a Jacobi pinv in
+    float64.  Sweep of the elbow towards full extension (rigid scene, no contacts): cond(J M^-1 J^T) runs from 1.4e2 to 1e5 and the
+    torques agree throughout -- bounds = 4x the maxima measured on a B200 (profiles/r02_osc_singularity.json, scripts/osc_singularity.py):
+    1e-4 N m uncoupled, 2.7e-4 coupled, 5.2e-3 at cond 1e5 (7.7e-5 of the torque)."""
+    from rui_b200.env import packed_model
+    cc = dict(CC_FIXED, uncouple_pos_ori=uncouple)
+    q4s = [-2.0, -1.0, -0.5, -0.3, -0.2, -0.15, -0.1, -0.08, -0.0705]
+    n = len(q4s)
+    env = _make(n, False, cc, seed=1)
+    env.reset()
+    q, v, w, t = [x.clone() for x in env.get_state()]
+    for i, q4 in enumerate(q4s):
+        q[i, :7] = torch.tensor([0.0, 0.3, 0.0, q4, 0.0, 1.2, 0.785])
+    env.set_state(qpos=q, task=t)
+    qn, vn, wn, tn = _np(*env.get_state())
+    act = np.tile(np.array([0.3, -0.2, 0.25, 0.1, -0.1, 0.05]), (n, 1))
+    orcs = []
+    for i in range(n):
+        e = O.OracleEnv(packed_model(False), abi.make_config(1, cc, control_freq=500), i)
+        e.reset()
+        e.set_state(qn[i], vn[i], wn[i], tn[i])
+        e.step(act[i])
+        orcs.append(e)
+    env.step(torch.as_tensor(act, dtype=torch.float32, device="cuda"))
+    tau = env.diag()[:, 13:20].cpu().numpy().astype(np.float64)
+    conds = []
+    for i, e in enumerate(orcs):
+        J, _, _ = e.eef()
+        cond = float(np.linalg.cond(J @ np.linalg.solve(e.M[:7, :7], J.T)))
+        conds.append(cond)
+        bound = (4e-4 if uncouple else 1.2e-3) if cond < 1e4 else 2e-2
+        assert np.abs(tau[i] - e.tau).max() <= bound, (q4s[i], cond, np.abs(tau[i] - e.tau).max())
+    assert max(conds) > 5e4  # the sweep does reach an ill-conditioned pose
+    env.close()
