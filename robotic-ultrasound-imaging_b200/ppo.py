@@ -191,6 +191,7 @@ class PPO:
         self._graphs = None
         # graphed update: hand-written backward pass (USIM_PPO_AUTOGRAD=1: autograd, for A/B measurements)
         self.manual_backward = os.environ.get("USIM_PPO_AUTOGRAD", "0") != "1"
+        self._splitk, self._ones_row, self._one = int(os.environ.get("USIM_PPO_SPLITK", "16")), None, None
         if os.environ.get("USIM_PPO_TF32", "0") == "1":  # developer knob: TF32 tensor-core GEMMs in the update (default: true fp32, as SB3)
             torch.backends.cuda.matmul.allow_tf32 = True
         self.norm = VecNormalizeState(self.N, self.obs_dim, self.device, gamma=gamma) if normalize else None
@@ -313,17 +314,31 @@ class PPO:
             h2 = torch.addmm(l2.bias, h1, l2.weight.t()).tanh_()
             return h1, h2, torch.addmm(head.bias, h2, head.weight.t())
 
+        # Weight gradients are [out, in] = g^T h with the BATCH as the contraction: a tall-skinny product whose output (at most
+        # 256 x 128) is a handful of tiles -- cuBLAS runs it on ~8 CTAs of 148 SMs (58 us for the 256 x 128 layer).  Split the batch
+        # into S slabs (one batched GEMM: S times the CTAs) and add the partial products.  Bias gradients ride on a GEMM with a row
+        # of ones instead of a column-reduction kernel.
+        S = self._splitk if B % self._splitk == 0 and B >= 64 * self._splitk else 1
+        if self._ones_row is None or self._ones_row.shape[1] != B:
+            self._ones_row = torch.ones(1, B, device=obs.device)
+
+        def wgrad(g, h, lin):
+            if S > 1:
+                torch.sum(torch.bmm(g.view(S, B // S, -1).transpose(1, 2), h.view(S, B // S, -1)), 0, out=lin.weight.grad)
+            else:
+                torch.mm(g.t(), h, out=lin.weight.grad)
+            torch.mm(self._ones_row, g, out=lin.bias.grad.view(1, -1))
+
         def backward(net, head, h1, h2, g_out):
             l1, l2 = net[0], net[2]
-            torch.mm(g_out.t(), h2, out=head.weight.grad)
-            torch.sum(g_out, 0, out=head.bias.grad)
+            wgrad(g_out, h2, head)
             g = torch.mm(g_out, head.weight).mul_(torch.addcmul(self._one, h2, h2, value=-1.0))  # through tanh: 1 - h^2
-            torch.mm(g.t(), h1, out=l2.weight.grad)
-            torch.sum(g, 0, out=l2.bias.grad)
+            wgrad(g, h1, l2)
             g = torch.mm(g, l2.weight).mul_(torch.addcmul(self._one, h1, h1, value=-1.0))
-            torch.mm(g.t(), obs, out=l1.weight.grad)
-            torch.sum(g, 0, out=l1.bias.grad)
+            wgrad(g, obs, l1)
 
+        if self._one is None:
+            self._one = torch.ones((), device=obs.device)
         p1, p2, mean = forward(pol.mlp_extractor.policy_net, pol.action_net)
         v1, v2, value = forward(pol.mlp_extractor.value_net, pol.value_net)
         value = value.squeeze(-1)
@@ -350,14 +365,25 @@ class PPO:
         backward(pol.mlp_extractor.value_net, pol.value_net, v1, v2, (verr * (2.0 * self.vf_coef / B)).unsqueeze(-1))
         return pl, vl, kl
 
+    def _pack(self, packed, batch):
+        od, ad = self.obs_dim, self.act_dim
+        packed[:, :od].copy_(batch[0]); packed[:, od:od + ad].copy_(batch[1])
+        packed[:, od + ad].copy_(batch[3]); packed[:, od + ad + 1].copy_(batch[4]); packed[:, od + ad + 2].copy_(batch[5])
+
     def _capture(self, batch):
         """Capture one minibatch step as two CUDA graphs sharing a memory pool: A = gather + forward + loss + backward + flat
         gradient bucket, B = (bucket / world) -> grads, clip, Adam.  Between them the bucket is all-reduced eagerly (NCCL)."""
         n, B, dev = batch[0].shape[0], self.batch_size, self.device
-        bufs = [torch.empty_like(x) for x in (batch[0], batch[1], batch[3], batch[4], batch[5])]  # obs, act, old_lp, adv, ret
-        for b, x in zip(bufs, (batch[0], batch[1], batch[3], batch[4], batch[5])):
-            b.copy_(x)
+        # the rollout as ONE packed array [n][obs | act | old_lp | adv | ret]: a minibatch is one row gather, its fields are column views
+        od, ad = self.obs_dim, self.act_dim
+        packed = torch.empty(n, od + ad + 3, device=dev)
+        self._pack(packed, batch)
         idx = torch.arange(B, device=dev)
+
+        def fields():
+            mb = packed[idx]
+            return mb[:, :od], mb[:, od:od + ad], mb[:, od + ad], mb[:, od + ad + 1], mb[:, od + ad + 2]
+
         params = [p for p in self.policy.parameters()]
         # the warm-up steps below are real optimiser steps on real data: put parameters and Adam state back afterwards
         saved_p = [p.detach().clone() for p in params]
@@ -373,14 +399,12 @@ class PPO:
             p.grad = flat_grad[off:off + k].view_as(p)
             off += k
 
-        self._one = torch.ones((), device=dev)
-
         def part_a():
             if self.manual_backward:  # every gradient entry is overwritten: no zeroing, no autograd graph
-                pl, vl, kl = self._manual_grads(bufs[0][idx], bufs[1][idx], bufs[2][idx], bufs[3][idx], bufs[4][idx])
+                pl, vl, kl = self._manual_grads(*fields())
             else:
                 flat_grad.zero_()
-                loss, pl, vl, kl = self._minibatch_loss(bufs[0][idx], bufs[1][idx], bufs[2][idx], bufs[3][idx], bufs[4][idx])
+                loss, pl, vl, kl = self._minibatch_loss(*fields())
                 loss.backward()
             for t, v in zip(stats, (pl, vl, kl)):
                 t.copy_(v.detach())
@@ -410,14 +434,13 @@ class PPO:
                 for k, v in st.items():
                     if torch.is_tensor(v):
                         v.copy_(saved_s[p][k]) if p in saved_s and k in saved_s[p] else v.zero_()
-        self._graphs = dict(a=ga, b=gb, flat=flat, idx=idx, bufs=bufs, stats=stats, n=n)
+        self._graphs = dict(a=ga, b=gb, flat=flat, idx=idx, packed=packed, stats=stats, n=n)
 
     def _train_graphed(self, batch):
         if self._graphs is None or self._graphs["n"] != batch[0].shape[0]:
             self._capture(batch)
         g = self._graphs
-        for b, x in zip(g["bufs"], (batch[0], batch[1], batch[3], batch[4], batch[5])):
-            b.copy_(x)
+        self._pack(g["packed"], batch)
         n = g["n"]
         for _ in range(self.n_epochs):
             perm = torch.randperm(n, device=self.device)
