@@ -332,9 +332,10 @@ def run_cuda(args):
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": per_gpu * env.action_dim * 4,
                     "d2h_bytes_per_step": per_gpu * (19 * 4 + 4 + 1),
-                    "note": "obs + reward + done every step; terminal observations only for the envs that finished in the step; "
-                            "early_termination off as in the device-resident line (with it on, as rl_config.yaml:53 trains, a few envs "
-                            "finish in every step and their terminal rows are fetched one by one: --early-termination)"},
+                    "note": "usim_step_host with page-locked host buffers: actions host->device by cudaMemcpyAsync; obs + reward + done "
+                            "rows (and the terminal rows of the envs that finished in the step) device->host as posted writes of the step "
+                            "kernel into the mapped result buffers, inside the timed region; stream synchronised every step.  "
+                            "early_termination off as in the device-resident line (rl_config.yaml:53 trains with it on: --early-termination)"},
             "gpu_launches": int(launches),
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

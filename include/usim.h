@@ -173,10 +173,15 @@ int usim_step(usim_handle* h, const float* act_dev, float* obs_dev, float* rew_d
 /* Convenience for host callers (the end-to-end path of bench.py and of the
  * single-env robosuite-style API): HOST buffers; the H2D/D2H copies are done
  * inside the call, which synchronises the library's stream.  A buffer that is
- * page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) is the DMA
- * end point itself; a pageable one is staged through the library's pinned
- * memory (one extra host memcpy).  tobs_host rows are written only for the envs
- * whose done flag is set in this step; the other rows are left untouched. */
+ * page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) is the
+ * transfer end point itself; a pageable one is staged through the library's
+ * pinned memory (one extra host memcpy).  Actions travel by cudaMemcpyAsync;
+ * observation, reward, done and terminal-observation rows are written by the
+ * step kernel straight into the page-locked result buffers (mapped host
+ * memory, one coalesced 76-byte row per env: posted PCIe writes that overlap
+ * the launch), so no device->host copy follows the kernel.  tobs_host rows are
+ * written only for the envs whose done flag is set in this step; the other rows
+ * are left untouched. */
 int usim_step_host(usim_handle* h, const float* act_host, float* obs_host, float* rew_host,
                    uint8_t* done_host, float* term_obs_host, int auto_reset);
 

@@ -59,6 +59,9 @@
 #ifndef WARP_SOLVE
 #define WARP_SOLVE 0 // 1: dense blocks of the preconditioner solved by one warp with shuffles (chol7_solve_warp2) instead of replicated in every thread.  Measured at 4096 envs: 0.441 ms vs 0.4245 ms replicated -- ~150 instead of ~290 instructions, but the 28 dependent shuffles are the longer chain and the kernel is latency bound: not kept
 #endif
+#ifndef SPLIT_SOLVE
+#define SPLIT_SOLVE (WPE == 2 && PREC3 && !WARP_SOLVE) // 1: the first warp solves the dense blocks while the second runs the first stencil pass of the slider block for all sliders (instead of both warps doing both)
+#endif
 #ifndef NORESTART
 #define NORESTART 1 // 1: keep the Polak-Ribiere direction across a preconditioner rebuild (flexible CG: beta uses the previous pg, made with the previous preconditioner) instead of restarting; measured 0.464 ms vs 0.485 ms
 #endif
@@ -868,6 +871,12 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
     }
     float b[6] = {0, 0, 0, 0, 0, 0};
 #else
+    float y[6] = {0, 0, 0, 0, 0, 0};
+    v3 yl = mk(0, 0, 0), yb = mk(0, 0, 0);
+    float b[6] = {0, 0, 0, 0, 0, 0};
+#if SPLIT_SOLVE
+    if (wrp == 0) {
+#endif
     float gd[13]; // dense part of the gradient
 #pragma unroll
     for (int k = 0; k < 13; k++) gd[k] = w.grad[k];
@@ -875,8 +884,6 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
 #pragma unroll
     for (int j = 0; j < 7; j++) ya[j] = gd[j];
     chol7_solve<7>(w.Pa, ya);
-    float y[6] = {0, 0, 0, 0, 0, 0};
-    v3 yl = mk(0, 0, 0), yb = mk(0, 0, 0);
     if (dm.soft) {
       float t9[9];
 #pragma unroll
@@ -887,7 +894,6 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
       yl = mtv(R, mk(y[0], y[1], y[2]));
       yb = mtv(R, mk(y[3], y[4], y[5])); // back to the body frame
     }
-    float b[6] = {0, 0, 0, 0, 0, 0};
     if (tid == 0) {
 #pragma unroll
       for (int j = 0; j < 7; j++) { w.pg[j] = ya[j]; b[0] += gd[j] * ya[j]; }
@@ -895,9 +901,27 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
         w.pg[7] = y[0]; w.pg[8] = y[1]; w.pg[9] = y[2]; w.pg[10] = yb.x; w.pg[11] = yb.y; w.pg[12] = yb.z;
         b[0] += gd[7] * y[0] + gd[8] * y[1] + gd[9] * y[2] + gd[10] * yb.x + gd[11] * yb.y + gd[12] * yb.z;
       }
+#if SPLIT_SOLVE
+#pragma unroll
+      for (int k = 0; k < 6; k++) w.yS[k] = y[k];
+#endif
     }
+#if SPLIT_SOLVE
+    } // (first warp)
+#endif
 #endif
 #if PREC3
+#if SPLIT_SOLVE
+    if (wrp == 1) { // (the whole pass by the second warp, while the first one solves)
+      PRAGMA_HOT
+      for (int i = lane; i < np; i += 32) {
+        const int4 e = pt.nb4[i];
+        float nb = w.Dp[e.x >> 16] * w.hs[13 + (e.x & 0x7fff)] + w.Dp[e.y >> 16] * w.hs[13 + (e.y & 0x7fff)] +
+                   w.Dp[e.z >> 16] * w.hs[13 + (e.z & 0x7fff)] + w.Dp[e.w >> 16] * w.hs[13 + (e.w & 0x7fff)];
+        w.pg[13 + i] = nb * w.dg[i];
+      }
+    }
+#else
     PRAGMA_HOT
     for (int i = tid; i < np; i += NT) {
       const int4 e = pt.nb4[i];
@@ -906,8 +930,15 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
       w.pg[13 + i] = nb * w.dg[i];
     }
 #endif
+#endif
 #if WARP_SOLVE || PREC3
     env_sync();
+#endif
+#if SPLIT_SOLVE
+    // the dense solution of the first warp, for everybody
+#pragma unroll
+    for (int k = 0; k < 6; k++) y[k] = w.yS[k];
+    yl = mtv(R, mk(y[0], y[1], y[2]));
 #endif
 #if WARP_SOLVE
     float y[6];
