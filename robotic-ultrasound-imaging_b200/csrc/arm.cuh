@@ -74,20 +74,20 @@ __device__ __forceinline__ void world_inertia(const float* R, const float* I6, f
   mm3(T, Rt, W);
 }
 
-// OSC goal update on the policy step (robosuite osc.set_goal), writes the task record
-__device__ __forceinline__ void osc_set_goal(const float* act, const ArmKin& k, float* ts) {
+// OSC goal update on the policy step (robosuite osc.set_goal), writes the task record; site / Rs: current grip-site pose
+__device__ __forceinline__ void osc_set_goal(const float* act, v3 site, const float* Rs, float* ts) {
   if (dm.mode == USIM_MODE_FIXED) {
     float d[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) d[i] = scale1(act[i], dm.in_min, dm.in_max, dm.out_min[i], dm.out_max[i]);
-    ts[USIM_TS_GOAL_POS + 0] = k.site.x + d[0];
-    ts[USIM_TS_GOAL_POS + 1] = k.site.y + d[1];
-    ts[USIM_TS_GOAL_POS + 2] = k.site.z + d[2];
+    ts[USIM_TS_GOAL_POS + 0] = site.x + d[0];
+    ts[USIM_TS_GOAL_POS + 1] = site.y + d[1];
+    ts[USIM_TS_GOAL_POS + 2] = site.z + d[2];
     if (d[3] != 0.f || d[4] != 0.f || d[5] != 0.f) {
       float ang = sqrtf(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
       float s = sinf(0.5f * ang) / ang, q[4] = {cosf(0.5f * ang), s * d[3], s * d[4], s * d[5]}, Rd[9], G[9];
       quat2mat(q, Rd);
-      mm3(Rd, k.Rs, G);
+      mm3(Rd, Rs, G);
 #pragma unroll
       for (int i = 0; i < 9; i++) ts[USIM_TS_GOAL_ORI + i] = G[i];
     }
@@ -193,7 +193,7 @@ ARM_LOOP
   } else {
     float av[7];
     for (int i = 0; i < dm.adim; i++) av[i] = act[i];
-    if (policy_step) osc_set_goal(av, k, ts);
+    if (policy_step) osc_set_goal(av, k.site, k.Rs, ts);
     float kp[6], kd[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) {

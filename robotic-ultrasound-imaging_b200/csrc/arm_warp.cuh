@@ -77,34 +77,6 @@ __device__ __forceinline__ void chol7_group(float* A, int j) {
     if (act && k <= j) A[j * 7 + k] = row[k];
 }
 
-// OSC goal update on the policy step (robosuite osc.set_goal), one lane; same arithmetic as arm.cuh osc_set_goal
-__device__ __forceinline__ void osc_set_goal_rec(const float* act, const float* ab, float* ts) {
-  if (dm.mode == USIM_MODE_FIXED) {
-    float d[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) d[i] = scale1(act[i], dm.in_min, dm.in_max, dm.out_min[i], dm.out_max[i]);
-    ts[USIM_TS_GOAL_POS + 0] = ab[AB_EEFPOS + 0] + d[0];
-    ts[USIM_TS_GOAL_POS + 1] = ab[AB_EEFPOS + 1] + d[1];
-    ts[USIM_TS_GOAL_POS + 2] = ab[AB_EEFPOS + 2] + d[2];
-    if (d[3] != 0.f || d[4] != 0.f || d[5] != 0.f) {
-      float ang = sqrtf(d[3] * d[3] + d[4] * d[4] + d[5] * d[5]);
-      float s = sinf(0.5f * ang) / ang, q[4] = {cosf(0.5f * ang), s * d[3], s * d[4], s * d[5]}, Rd[9], G[9];
-      quat2mat(q, Rd);
-      mm3(Rd, ab + AB_EEFR, G);
-#pragma unroll
-      for (int i = 0; i < 9; i++) ts[USIM_TS_GOAL_ORI + i] = G[i];
-    }
-  } else if (dm.mode != USIM_MODE_WRENCH) {
-    ts[USIM_TS_GOAL_POS + 0] = ts[USIM_TS_TRAJ_PT + 0];
-    ts[USIM_TS_GOAL_POS + 1] = ts[USIM_TS_TRAJ_PT + 1];
-    ts[USIM_TS_GOAL_POS + 2] = ts[USIM_TS_TRAJ_PT + 2] + (dm.mode == USIM_MODE_VARIABLE_Z ? scale1(act[6], -1.f, 1.f, -0.05f, 0.05f) : 0.f);
-    float G[9];
-    goal_mat(G);
-#pragma unroll
-    for (int i = 0; i < 9; i++) ts[USIM_TS_GOAL_ORI + i] = G[i];
-  }
-}
-
 // One env step of the arm (controller runs), by the 8 lanes of a group; j = lane within the group.
 //   q, qd      joint position / velocity of joint j (lanes j < 7; anything elsewhere)
 //   act        the env's action row (global)
@@ -248,7 +220,7 @@ __device__ __forceinline__ void arm_forward_group(bool policy_step, float q, flo
   // ---------------- OSC_POSE torques [SURVEY App. C.2/C.3]
   float av[7];
   for (int i = 0; i < dm.adim; i++) av[i] = act[i];
-  if (j == 0 && policy_step && live) osc_set_goal_rec(av, ab, ts);
+  if (j == 0 && policy_step && live) osc_set_goal(av, ld3(ab + AB_EEFPOS), ab + AB_EEFR, ts);
   // factor of M (row per lane) while lane 0 writes the goal
   if (j < 7) {
 #pragma unroll

@@ -291,15 +291,22 @@ class PPO:
                 if trace is not None:
                     ret_trace[t].copy_(trace)
             self._last_obs = st["obs"].clone()
-            last_v = self.policy(self.norm.normalize_obs(self._last_obs) if self.norm else self._last_obs)[1]
-            if self.norm is not None:
-                self.norm.ret_rms.update(ret_trace, sync=True)
-                rew_n = self.norm.normalize_reward(rew_b)
-                self.norm.obs_rms.update(raw_b, sync=True)
-            else:
-                rew_n = rew_b
-            adv, ret = compute_gae(rew_n, val_b, done_b, last_v, self.gamma, self.lam)
-        ep_r, ep_l, ep_n = allreduce_episode_stats(st["ep_r"].clone(), st["ep_l"].clone(), st["ep_n"].clone())
+        return self._finish_rollout(obs_b, raw_b, act_b, rew_b, val_b, logp_b, done_b, ret_trace, st["ep_r"].clone(), st["ep_l"].clone(), st["ep_n"].clone())
+
+    @torch.no_grad()
+    def _finish_rollout(self, obs_b, raw_b, act_b, rew_b, val_b, logp_b, done_b, ret_trace, ep_r, ep_l, ep_n):
+        """Bootstrap value, one merge of the rollout's moments (NCCL all-reduce when world > 1), reward normalisation, GAE, statistics."""
+        T, N = rew_b.shape
+        obs = self._last_obs
+        last_v = self.policy(self.norm.normalize_obs(obs) if self.norm else obs)[1]
+        if self.norm is not None:
+            self.norm.ret_rms.update(ret_trace, sync=True)
+            rew_n = self.norm.normalize_reward(rew_b)
+            self.norm.obs_rms.update(raw_b, sync=True)
+        else:
+            rew_n = rew_b
+        adv, ret = compute_gae(rew_n, val_b, done_b, last_v, self.gamma, self.lam)
+        ep_r, ep_l, ep_n = allreduce_episode_stats(ep_r, ep_l, ep_n)
         self.num_timesteps += T * N * self.world
         self.last_stats.update(ep_rew_mean=float(ep_r / ep_n) if ep_n > 0 else float("nan"),
                                ep_len_mean=float(ep_l / ep_n) if ep_n > 0 else float("nan"), episodes=float(ep_n),
@@ -338,22 +345,7 @@ class PPO:
                 self.ep_len *= 1 - dm
                 obs = o.clone()
             self._last_obs = obs
-            last_v = self.policy(self.norm.normalize_obs(obs) if self.norm else obs)[1]
-            if self.norm is not None:
-                # one merge of the rollout's moments (NCCL all-reduce when world > 1), then normalise the stored rewards
-                self.norm.ret_rms.update(ret_trace, sync=True)
-                rew_n = self.norm.normalize_reward(rew_b)
-                self.norm.obs_rms.update(raw_b, sync=True)
-            else:
-                rew_n = rew_b
-            adv, ret = compute_gae(rew_n, val_b, done_b, last_v, self.gamma, self.lam)
-        ep_r, ep_l, ep_n = allreduce_episode_stats(ep_r, ep_l, ep_n)
-        self.num_timesteps += T * N * self.world
-        self.last_stats.update(ep_rew_mean=float(ep_r / ep_n) if ep_n > 0 else float("nan"),
-                               ep_len_mean=float(ep_l / ep_n) if ep_n > 0 else float("nan"), episodes=float(ep_n),
-                               step_reward_mean=float(rew_b.mean()))
-        flat = lambda x: x.reshape(T * N, *x.shape[2:])
-        return flat(obs_b), flat(act_b), flat(val_b), flat(logp_b), flat(adv), flat(ret)
+        return self._finish_rollout(obs_b, raw_b, act_b, rew_b, val_b, logp_b, done_b, ret_trace, ep_r, ep_l, ep_n)
 
     # ------------------------------------------------------------------ update
     def _allreduce_grads(self):
