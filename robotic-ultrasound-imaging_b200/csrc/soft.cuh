@@ -57,10 +57,13 @@
 #define ARM_SHIFT 1
 #endif
 #ifndef WARP_SOLVE
-#define WARP_SOLVE 0 // 1: dense blocks of the preconditioner solved by one warp with shuffles (chol7_solve_warp2) instead of replicated in every thread.  Measured at 4096 envs: 0.441 ms vs 0.4245 ms replicated -- ~150 instead of ~290 instructions, but the 28 dependent shuffles are the longer chain and the kernel is latency bound: not kept
+#define WARP_SOLVE 0 // 1: dense blocks of the preconditioner solved by one warp with shuffles (chol7_solve_warp2) instead of replicated in every thread.  Measured at 4096 envs: 0.441 ms vs 0.4245 ms replicated -- ~150 instead of ~290 instructions, but the 28 dependent shuffles are the longer chain and the kernel is latency bound: not kept.  Re-measured with the first stencil pass on the second warp (SPLIT_Z1): 0.5064 vs 0.4993 ms
 #endif
 #ifndef SPLIT_SOLVE
 #define SPLIT_SOLVE (WPE == 2 && PREC3 && !WARP_SOLVE) // 1: the first warp solves the dense blocks while the second runs the first stencil pass of the slider block for all sliders (instead of both warps doing both)
+#endif
+#ifndef SPLIT_Z1
+#define SPLIT_Z1 (SPLIT_SOLVE || (WARP_SOLVE && WPE == 2 && PREC3)) // the first stencil pass belongs to the second warp alone
 #endif
 #ifndef NORESTART
 #define NORESTART 1 // 1: keep the Polak-Ribiere direction across a preconditioner rebuild (flexible CG: beta uses the previous pg, made with the previous preconditioner) instead of restarting; measured 0.464 ms vs 0.485 ms
@@ -76,11 +79,17 @@
 // trades ILP against the size of the loop body in the instruction cache (`no_instruction` is the top stall with 16 warps per SM)
 #define USIM_STR2(x) #x
 #define USIM_STR(x) USIM_STR2(x)
-// measured, 4096 envs: compiler default 6.52 M steps/s (7456 SASS instructions), unroll 1: 6.61 M (7096), unroll 2: 5.79 M (8296)
+// measured, 4096 envs: compiler default 6.52 M steps/s (7456 SASS instructions), unroll 1: 6.61 M (7096), unroll 2: 5.79 M (8296);
+// final kernel of round 2: unroll 1 7.87 M, the per-slider loops alone x2 (HOT_UNROLL_S=2) 7.31 M, every hot loop x2 5.11 M -- the
+// loop body sits at the edge of the instruction cache: +400 instructions cost 8 %, +1200 cost 35 %
 #ifndef HOT_UNROLL
 #define HOT_UNROLL 1
 #endif
 #define PRAGMA_HOT _Pragma(USIM_STR(unroll HOT_UNROLL))
+#ifndef HOT_UNROLL_S
+#define HOT_UNROLL_S HOT_UNROLL // the per-slider / per-unknown loops alone (4-5 trips per warp); the per-contact loops run 1-2 trips
+#endif
+#define PRAGMA_HOT_S _Pragma(USIM_STR(unroll HOT_UNROLL_S))
 
 struct __align__(16) WS {
   // ---- landing zones of the 1-D TMA bulk copies (whole HBM rows, 16-byte aligned; written back the same way) ----
@@ -697,7 +706,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
     if (dm.soft) {
       const v3 ivl = mtv(R, ld3(in + 7)); // R^T in_v
       const float Dt = w.Dt, dts = Dt * S4[0];
-      PRAGMA_HOT
+      PRAGMA_HOT_S
       for (int i = tid; i < np; i += NT) {
         float xi = in[13 + i];
         v3 ah = xyz(pt.ax4[i]);
@@ -833,7 +842,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
     float a[11];
 #pragma unroll
     for (int k = 0; k < 11; k++) a[k] = 0.f;
-    PRAGMA_HOT
+    PRAGMA_HOT_S
     for (int i = tid; i < np; i += NT) {
       float g = w.grad[13 + i], gi = g * w.dg[i];
       v3 ah = xyz(pt.ax4[i]);
@@ -911,9 +920,9 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
 #endif
 #endif
 #if PREC3
-#if SPLIT_SOLVE
+#if SPLIT_Z1
     if (wrp == 1) { // (the whole pass by the second warp, while the first one solves)
-      PRAGMA_HOT
+      PRAGMA_HOT_S
       for (int i = lane; i < np; i += 32) {
         const int4 e = pt.nb4[i];
         float nb = w.Dp[e.x >> 16] * w.hs[13 + (e.x & 0x7fff)] + w.Dp[e.y >> 16] * w.hs[13 + (e.y & 0x7fff)] +
@@ -922,7 +931,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
       }
     }
 #else
-    PRAGMA_HOT
+    PRAGMA_HOT_S
     for (int i = tid; i < np; i += NT) {
       const int4 e = pt.nb4[i];
       float nb = w.Dp[e.x >> 16] * w.hs[13 + (e.x & 0x7fff)] + w.Dp[e.y >> 16] * w.hs[13 + (e.y & 0x7fff)] +
@@ -954,7 +963,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
       if (tid < 7 || dm.soft) b[0] += w.grad[tid] * pgk;
     }
 #endif
-    PRAGMA_HOT
+    PRAGMA_HOT_S
     for (int i = tid; i < np; i += NT) {
       float g = w.grad[13 + i];
       v3 ah = xyz(pt.ax4[i]);
@@ -1159,7 +1168,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
     float hx2 = 0.f, rhs2 = 0.f;
     if (init) {
       // grad holds rhs until here
-      PRAGMA_HOT
+      PRAGMA_HOT_S
       for (int i = tid; i < nv; i += NT) {
         float r = w.grad[i], hx = w.Hx[i] - r;
         w.Hx[i] = hx; w.grad[i] = hx;
@@ -1206,7 +1215,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
         if (an == alpha) break;
         alpha = an;
       }
-      PRAGMA_HOT
+      PRAGMA_HOT_S
       for (int i = tid; i < nv; i += NT) {
         float hx = w.Hx[i] + alpha * w.hs[i];
         w.x[i] += alpha * w.s[i]; w.Hx[i] = hx; w.grad[i] = hx;
@@ -1235,7 +1244,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
     gpg = gpn;
 #pragma unroll
     for (int k = 0; k < 4; k++) S4[k] = -rd(w.rq, 2 + k) + beta * S4[k];
-    PRAGMA_HOT
+    PRAGMA_HOT_S
 #if PREC3
     for (int i = tid; i < nv; i += NT) {
       float p = i >= 13 ? w.hs[i] : w.pg[i];
