@@ -65,6 +65,9 @@
 #ifndef SPLIT_Z1
 #define SPLIT_Z1 (SPLIT_SOLVE || (WARP_SOLVE && WPE == 2 && PREC3)) // the first stencil pass belongs to the second warp alone
 #endif
+#ifndef USIM_TRACE
+#define USIM_TRACE 0 // 1 (developer build, scripts/trace_tail.py): every work item records (start ns, end ns, SM id) when the USIM_TRACE=<file> environment variable is set
+#endif
 #ifndef NORESTART
 #define NORESTART 1 // 1: keep the Polak-Ribiere direction across a preconditioner rebuild (flexible CG: beta uses the previous pg, made with the previous preconditioner) instead of restarting; measured 0.464 ms vs 0.485 ms
 #endif
@@ -100,6 +103,7 @@ struct __align__(16) WS {
   float ab[ARMBUF];
   float ts[USIM_TASK_DIM];
   unsigned long long bar;                              // mbarrier of the load
+  unsigned long long t0;                               // developer trace: start time of this work item
   // ----
   float dg[NPART_MAX], dgm[NPART_MAX];                 // dg: slider diagonal of the preconditioner, stored INVERTED; dgm: M+E diagonal w/o tendon
   float Dp[NPAIR_MAX];                                 // D of each "smooth" pair
@@ -354,6 +358,7 @@ struct SolveArgs {
   float *slot_qpos, *slot_task, *slot_obs; // [2][n][QPAD | USIM_TASK_DIM | SLOT_OBS]
   int *req_list, *req_cnt;         // (env, episode number) pairs to prepare, appended by this launch
   const int *prep_items, *prep_n;  // prepare mode: the requests this launch works through
+  unsigned long long* trace;       // developer trace (USIM_TRACE): per env (start ns, end ns, SM id) of the launch, nullptr: off
   int* queue;                      // persistent launch (grid = resident CTAs): next launch slot, fetched with atomicAdd (nullptr: item = blockIdx.x + k gridDim.x)
 };
 
@@ -380,6 +385,9 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
     item = w.item;
   }
   if (item >= nitems) break;
+#if USIM_TRACE
+  if (a.trace && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w.t0));
+#endif
   int env = item;
   float *qp_g, *qv_g, *wm_g, *ts_g, *obs_row;
   const float* ab_g;
@@ -1496,5 +1504,14 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
     }
   }
   env_sync();
+#if USIM_TRACE
+  if (a.trace && tid == 0) {
+    unsigned long long t_end;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.trace[3 * (size_t)env] = w.t0; a.trace[3 * (size_t)env + 1] = t_end; a.trace[3 * (size_t)env + 2] = smid;
+  }
+#endif
   } // work items
 }

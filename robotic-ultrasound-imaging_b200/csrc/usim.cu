@@ -52,6 +52,8 @@ struct usim_handle {
   // launch order of the solve kernel (longest solve first): bins filled by launch T, flattened by the arm kernel of launch T + 1
   int *bin_cnt = nullptr, *bin_items = nullptr, *order = nullptr; // [2][NBIN], [2][NBIN][n], [n]
   int* queue = nullptr;  // work queue of a persistent step launch (next launch slot)
+  unsigned long long* trace = nullptr;  // developer trace of the step launches (USIM_TRACE=<file>): [n][3] = start ns, end ns, SM id
+  std::string trace_path;
   int step_grid = 0;     // CTAs of a step launch: every resident slot of the device once (0: one CTA per env)
   int64_t solve_tick = 0;
   // reset pipeline: two prepared reset states per env (slot k holds an episode number of parity k), made on a side stream
@@ -285,6 +287,11 @@ int usim_create(const usim_model* m, const usim_config* c, int device, usim_hand
   if (const char* at = getenv("USIM_ARM_THREAD")) h->arm_thread = atoi(at) != 0;
   if (const char* hc = getenv("USIM_HOST_COPY")) h->host_copy = atoi(hc) != 0;
   h->smem = sizeof(WS);
+  if (const char* tp = getenv("USIM_TRACE")) { // developer knob: the last step launch's per-env timeline is written to this file at destroy
+    h->trace_path = tp;
+    CKH(cudaMalloc((void**)&h->trace, (size_t)h->n * 3 * sizeof(unsigned long long)));
+    CKH(cudaMemset(h->trace, 0, (size_t)h->n * 3 * sizeof(unsigned long long)));
+  }
   if (const char* pg = getenv("USIM_PERSISTENT")) { // developer knob: persistent step launch, one CTA per resident slot
     int per_sm = 0;
     if (atoi(pg) != 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solve_kernel, NT, sizeof(WS)) == cudaSuccess && per_sm > 0)
@@ -302,6 +309,13 @@ int usim_destroy(usim_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   if (g_active == h) g_active = nullptr;
+  if (h->trace) {
+    std::vector<unsigned long long> t((size_t)h->n * 3);
+    if (cudaMemcpy(t.data(), h->trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      if (FILE* f = fopen(h->trace_path.c_str(), "wb")) { fwrite(t.data(), sizeof(unsigned long long), t.size(), f); fclose(f); }
+    }
+    cudaFree(h->trace);
+  }
   for (auto& p : h->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   void* dev[] = {h->counters, h->qpos, h->qvel, h->warm, h->task, h->armbuf, h->diag, h->ncon, h->geom1, h->geom2, h->cdist, h->ax4,
                  h->ps4, h->nb4, h->eq_pairs, h->d_act, h->d_obs, h->d_tobs, h->d_rew,
@@ -417,6 +431,7 @@ static int launch_step(usim_handle* h, const float* act, float* obs, float* rew,
     a.obs = obs; a.rew = rew; a.done = done; a.tobs = tobs;
     a.order = h->order; a.bin_cnt = h->bin_cnt + b * NBIN; a.bin_items = h->bin_items + (size_t)b * NBIN * n;
     a.queue = h->step_grid ? h->queue : nullptr;
+    a.trace = h->trace;
     if (last && auto_reset) {
       if (producer_begin(h, s)) return -1;
       a.auto_reset = 1;
