@@ -26,6 +26,9 @@
 #ifndef WPE
 #define WPE 2
 #endif
+#ifndef USIM_TRACE
+#define USIM_TRACE 0 // 1 (developer build, scripts/trace_tail.py): every work item records (start ns, end ns, SM id) when the USIM_TRACE=<file> environment variable is set
+#endif
 #define NT (32 * WPE)
 #ifndef MINB
 #define MINB (WPE <= 2 ? 8 : 16 / WPE) // resident CTAs per SM the register allocation is sized for
@@ -65,9 +68,6 @@
 #ifndef SPLIT_Z1
 #define SPLIT_Z1 (SPLIT_SOLVE || (WARP_SOLVE && WPE == 2 && PREC3)) // the first stencil pass belongs to the second warp alone
 #endif
-#ifndef USIM_TRACE
-#define USIM_TRACE 0 // 1 (developer build, scripts/trace_tail.py): every work item records (start ns, end ns, SM id) when the USIM_TRACE=<file> environment variable is set
-#endif
 #ifndef NORESTART
 #define NORESTART 1 // 1: keep the Polak-Ribiere direction across a preconditioner rebuild (flexible CG: beta uses the previous pg, made with the previous preconditioner) instead of restarting; measured 0.464 ms vs 0.485 ms
 #endif
@@ -103,7 +103,9 @@ struct __align__(16) WS {
   float ab[ARMBUF];
   float ts[USIM_TASK_DIM];
   unsigned long long bar;                              // mbarrier of the load
+#if USIM_TRACE
   unsigned long long t0;                               // developer trace: start time of this work item
+#endif
   // ----
   float dg[NPART_MAX], dgm[NPART_MAX];                 // dg: slider diagonal of the preconditioner, stored INVERTED; dgm: M+E diagonal w/o tendon
   float Dp[NPAIR_MAX];                                 // D of each "smooth" pair
