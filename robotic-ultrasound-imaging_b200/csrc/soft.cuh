@@ -49,8 +49,12 @@
 #ifndef PREC3
 #define PREC3 1
 #endif
+// Re-measured on the final kernel of round 2 (calibrated probe, line-search tolerance 0.03; kernel ms / CG iterations): 0.9: 0.487 / 5.31,
+// 1.0: 0.479 / 5.32, 1.1: 0.480 / 5.33, 1.2: 0.479 / 5.34, 1.3: 0.483 / 5.37, 1.4: 0.483 / 5.41, 1.5: 0.485 / 5.45, 1.6: 0.486 / 5.50,
+// 1.8: 0.497 / 5.65 -- the optimum is a plateau from the plain Neumann series (1.0) to 1.2: the contact terms on the diagonal have
+// lowered the effective rho.
 #ifndef CHEB_C
-#define CHEB_C 1.6f
+#define CHEB_C 1.1f
 #endif
 // Arm part of the warm start: the previous qacc shifted by M^-1 (qfrc_smooth_now - qfrc_smooth_previous), computed by the arm kernel
 // with the Cholesky factor it holds anyway.  A fresh action every step moves qfrc_smooth of the arm by the change of the controller
@@ -72,8 +76,11 @@
 #define NORESTART 1 // 1: keep the Polak-Ribiere direction across a preconditioner rebuild (flexible CG: beta uses the previous pg, made with the previous preconditioner) instead of restarting; measured 0.464 ms vs 0.485 ms
 #endif
 #ifndef LS_TOL
-#define LS_TOL 1e-3f // line search: stop when |phi'| has dropped by this factor (1e-5 cost one more evaluation per iteration for
-                     // nothing in fp32: 0.464 ms; 1e-3: 0.431 ms, 1e-2: 0.430 ms, same iteration count)
+#define LS_TOL 0.03f // line search: stop when |phi'| has dropped by this factor.  An inexact search is enough for nonlinear CG (the
+                     // converged solution does not depend on it, only the path).  Measured at 4096 envs on the final kernel of round 2
+                     // (kernel ms / CG iterations / line-search evaluations per env-step): 1e-3: 0.498 / 5.45 / 13.2, 1e-2: 0.490 / 5.47 / 12.1,
+                     // 0.02: 0.488 / 5.48 / 11.9, 0.03: 0.487 / 5.50 / 11.85, 0.05: 0.487 / 5.52 / 11.75, 0.1: 0.488 / 5.57 / 11.7, 0.3: 0.501 / 5.64 / 11.7
+                     // (round 1: 1e-5 cost one more evaluation per iteration for nothing in fp32)
 #endif
 #ifndef LS_MAX
 #define LS_MAX 8 // evaluations of phi'(alpha) per line search (Newton with bracketing; 1 = one quadratic step, unverified)
@@ -440,7 +447,11 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
   if (tid < 7) {
     w.qdarm[tid] = w.hs[tid];
 #if ARM_SHIFT
+#ifdef ARM_SHIFT_SCALE // developer knob: damped shift (in contact M^-1 over-estimates the response of the arm)
+    if (mode != 1) w.x[tid] += ARM_SHIFT_SCALE * w.ab[AB_DX + tid];
+#else
     if (mode != 1) w.x[tid] += w.ab[AB_DX + tid]; // warm start of the arm follows the change of its applied force (arm kernel)
+#endif
 #endif
   }
   float quat[4] = {1, 0, 0, 0};
