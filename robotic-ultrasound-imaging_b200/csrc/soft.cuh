@@ -1249,7 +1249,21 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
       // (no barrier, as above)
     }
     update_grad(hx2, rhs2);
-    const bool changed = rd(w.rg, 12) > 0.f;
+    // Rebuild policy.  A rebuild costs as much as ~0.8 CG passes (two Hessian passes over the contacts, three 21-value reductions, two
+    // factorisations) and most zone changes of the first iterations are light contacts flickering: rebuilding on every change
+    // (round 1) buys 0.5 iteration for 1.6 rebuilds per solve.  Shipped: no rebuild during the first REBUILD_LATE iterations unless at
+    // least REBUILD_MIN contacts changed zone; from then on every change rebuilds (a solve that is still running is a hard one: without
+    // the late rebuilds the iteration tail grows, P(>= 20 iterations) 2.5e-4 -> 3.6e-3).  Measured at 4096 envs (kernel ms / iterations /
+    // rebuilds per solve / P(>= 40 iterations)):  always 0.481 / 5.33 / 1.63 / 8e-6;  MIN 2, 3, 4, 6 without LATE: 0.468, 0.465, 0.462,
+    // 0.460 (6.05 / 0.12 / 7e-5);  never 0.469 / 6.17 / 0 / -;  MIN 4 LATE 5: 0.450;  MIN 6 LATE 5: 0.444;  none before LATE = 6, 5, 4, 3:
+    // 0.449, 0.445, 0.442 (5.91 / 0.15 / 1.7e-5), 0.4415 (5.79 / 0.27 / 1.5e-5).
+#ifndef REBUILD_MIN
+#define REBUILD_MIN 1000
+#endif
+#ifndef REBUILD_LATE
+#define REBUILD_LATE 3
+#endif
+    const bool changed = rd(w.rg, 12) >= (it < REBUILD_LATE ? (float)REBUILD_MIN : 1.f);
     hxn = sqrtf(rd(w.rg, 13));
     if (init) rhsn = sqrtf(rd(w.rg, 14));
     bool restart = init;
