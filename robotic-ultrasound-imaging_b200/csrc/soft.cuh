@@ -46,8 +46,11 @@
 // of N.  rho ~ 0.7 for this model (sum of a slider's pair D over its diagonal) -> c = 1.6; measured at 4096 envs:
 // second order 0.513 ms, c = 1.0 (plain Neumann) 0.513, 1.4: 0.485, 1.7: 0.483, 2.0: 0.488, 2.4: 0.506, 3.0: 0.578;
 // fourth order (three stencil passes, a0 (z0 + z1) + a2 (z2 + z3)): 0.488 ms vs 0.464 for the cubic -- not kept.
+// Round 2, after the rebuild policy (most solves keep the preconditioner of their warm start): the SECOND-order block does as well as the
+// cubic in iterations and saves a stencil pass -- PREC3 = 0: 0.428 ms / 5.73 iterations, PREC3 = 1 (c = 1.1): 0.442 / 5.79; Jacobi
+// (PREC_JACOBI): 0.473 / 7.05; weight 0.8 / 1.2 / 1.4 on the first-order term (PREC2_C): 0.441 / 0.449 / 0.503.
 #ifndef PREC3
-#define PREC3 1
+#define PREC3 0
 #endif
 // Re-measured on the final kernel of round 2 (calibrated probe, line-search tolerance 0.03; kernel ms / CG iterations): 0.9: 0.487 / 5.31,
 // 1.0: 0.479 / 5.32, 1.1: 0.480 / 5.33, 1.2: 0.479 / 5.34, 1.3: 0.483 / 5.37, 1.4: 0.483 / 5.41, 1.5: 0.485 / 5.45, 1.6: 0.486 / 5.50,
@@ -68,6 +71,9 @@
 #endif
 #ifndef SPLIT_SOLVE
 #define SPLIT_SOLVE (WPE == 2 && PREC3 && !WARP_SOLVE) // 1: the first warp solves the dense blocks while the second runs the first stencil pass of the slider block for all sliders (instead of both warps doing both)
+#endif
+#ifndef SPLIT_DENSE
+#define SPLIT_DENSE 0 // 1 (needs WPE == 2, PREC3 == 0): the first warp solves the 7x7 arm block, the second the 6x6 torso block, one more barrier, instead of both warps solving both.  Measured: 0.4280 vs 0.4281 ms -- parity green, no gain, not shipped
 #endif
 #ifndef SPLIT_Z1
 #define SPLIT_Z1 (SPLIT_SOLVE || (WARP_SOLVE && WPE == 2 && PREC3)) // the first stencil pass belongs to the second warp alone
@@ -904,6 +910,42 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
     float y[6] = {0, 0, 0, 0, 0, 0};
     v3 yl = mk(0, 0, 0), yb = mk(0, 0, 0);
     float b[6] = {0, 0, 0, 0, 0, 0};
+#if SPLIT_DENSE
+    if (wrp == 0) { // arm block
+      float ga[7], ya[7];
+#pragma unroll
+      for (int j = 0; j < 7; j++) { ga[j] = w.grad[j]; ya[j] = ga[j]; }
+      chol7_solve<7>(w.Pa, ya);
+      if (tid == 0) {
+#pragma unroll
+        for (int j = 0; j < 7; j++) { w.pg[j] = ya[j]; b[0] += ga[j] * ya[j]; }
+      }
+    } else { // torso block (world frame), for everybody through yS
+      if (dm.soft) {
+        float gt[6], t9[9];
+#pragma unroll
+        for (int k = 0; k < 6; k++) gt[k] = w.grad[7 + k];
+#pragma unroll
+        for (int k = 0; k < 9; k++) t9[k] = rd(w.rp, k);
+        v3 tv = mp * mv(R, ld3(t9)) + ld3(t9 + 3), gw = mv(R, mk(gt[3], gt[4], gt[5])) - ld3(t9 + 6);
+        y[0] = gt[0] - tv.x; y[1] = gt[1] - tv.y; y[2] = gt[2] - tv.z; y[3] = gw.x; y[4] = gw.y; y[5] = gw.z;
+        chol7_solve<6>(w.Sf, y);
+        yb = mtv(R, mk(y[3], y[4], y[5])); // back to the body frame
+        if (lane == 0) {
+          w.pg[7] = y[0]; w.pg[8] = y[1]; w.pg[9] = y[2]; w.pg[10] = yb.x; w.pg[11] = yb.y; w.pg[12] = yb.z;
+          b[0] += gt[0] * y[0] + gt[1] * y[1] + gt[2] * y[2] + gt[3] * yb.x + gt[4] * yb.y + gt[5] * yb.z;
+        }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) w.yS[k] = y[k];
+      }
+    }
+    env_sync();
+#pragma unroll
+    for (int k = 0; k < 6; k++) y[k] = w.yS[k];
+    yl = mtv(R, mk(y[0], y[1], y[2]));
+#else
 #if SPLIT_SOLVE
     if (wrp == 0) {
 #endif
@@ -939,6 +981,7 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
 #if SPLIT_SOLVE
     } // (first warp)
 #endif
+#endif // SPLIT_DENSE
 #endif
 #if PREC3
 #if SPLIT_Z1
@@ -1001,9 +1044,17 @@ __global__ void __launch_bounds__(NT, MINB) solve_kernel(const SolveArgs a) {
       float p = w.hs[13 + i] + CHEB_C * (w.pg[13 + i] + nb * w.dg[i]) - by * w.dg[i];
       w.hs[13 + i] = p; // neighbours read pg in this pass, not hs
 #else
+#ifdef PREC_JACOBI // developer knob: diagonal slider block (no stencil pass at all)
+      float nb = 0.f;
+#else
       float nb = w.Dp[e.x >> 16] * w.hs[13 + (e.x & 0x7fff)] + w.Dp[e.y >> 16] * w.hs[13 + (e.y & 0x7fff)] +
                  w.Dp[e.z >> 16] * w.hs[13 + (e.z & 0x7fff)] + w.Dp[e.w >> 16] * w.hs[13 + (e.w & 0x7fff)];
+#endif
+#ifdef PREC2_C // developer knob: weight of the first-order term of the second-order slider block
+      float p = w.hs[13 + i] + (PREC2_C * nb - by) * w.dg[i];
+#else
       float p = w.hs[13 + i] + (nb - by) * w.dg[i];
+#endif
       w.pg[13 + i] = p;
 #endif
       b[0] += g * p; b[2] += p;
