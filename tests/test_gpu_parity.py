@@ -124,7 +124,10 @@ def test_config2_rigid_press_trajectory_parity(O):
 # velocity 1.2e-4, Fz mean 3.3e-3 rel, dFz 4.5e-3 rel, pose error 5.4e-6 / 5.9e-6).  force_rel: |dF| / max(1 N, |F|); torque_rel:
 # / max(0.1 Nm, |T|); dfz_rel: / max(500, |dFz|) (dFz = dF x 500 Hz).  They hold on every env-step whose contact lists agree on the
 # two sides (parity_util.compare_rollout); TOL_ALL bounds the remaining ones, where a contact crosses zero distance one step apart.
-TOL_SOFT = dict(qpos=3e-5, qvel=1.2e-3, reward=6e-2, force_rel=8e-3, torque_rel=1.5e-2, obs_eef_vel=4e-4, fz_mean_rel=1e-2, dfz_rel=1.5e-2,
+# dfz_rel: dFz = (Fz - Fz_prev) * control_freq (ultrasound.py:542) is the x500 finite difference of a force that agrees to ~1e-3 relative: it
+# follows where inside the solver's tolerance ball the two solutions land.  Measured maxima over the scenarios and solver policies of
+# round 2: 1.5e-3 ... 1.7e-2 (UR5e, 40 steps); bound 2.4x the largest.
+TOL_SOFT = dict(qpos=3e-5, qvel=1.2e-3, reward=6e-2, force_rel=8e-3, torque_rel=1.5e-2, obs_eef_vel=4e-4, fz_mean_rel=1e-2, dfz_rel=4e-2,
                 obs_vel_mean=2e-5, obs_pos_err=2e-5, obs_quat_err=2e-5, ts_traj_pt=1e-7, ts_pos_err=4e-3, ts_ori_err=1e-3)
 TOL_ALL = dict(qpos=3e-5, qvel=3e-3, force_rel=0.3, obs_pos_err=2e-5, obs_quat_err=2e-5)
 
