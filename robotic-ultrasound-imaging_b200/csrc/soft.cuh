@@ -1,4 +1,4 @@
-// soft.cuh — K3..K9 fused: one WARP per env, the whole env state staged in shared memory.
+// soft.cuh — K3..K9 fused: one CTA of two warps per env, the whole env state staged in shared memory.
 //
 //   K3 torso kinematics + inertia + bias   (free body + 270 radial sliders, arrow-structured M)
 //   K4 collision: table<->particle, probe<->particle, table<->probe, deterministic MuJoCo ordering
@@ -14,7 +14,7 @@
 //
 // Structure of one CG iteration (every dot product rides on a pass that exists anyway; 5 warp reductions):
 //   applyH(s) [+ s.Hx, s.Hs]  ->  contact rows J s  ->  line search (Newton on phi')  ->  x, Hx, grad, jar updates [+ |Hx|^2]
-//   ->  contact forces into grad [+ probe wrench, zone changes]  ->  (preconditioner rebuild if the active set moved)
+//   ->  contact forces into grad [+ probe wrench, zone changes]  ->  (preconditioner rebuild if the active set moved, from the fourth iteration on)
 //   ->  pg = P^-1 grad [+ grad.pg_old, grad.pg, |grad|^2, the slider sums of pg that the next applyH needs]  ->  s = -pg + beta s
 #pragma once
 #include "common.cuh"
