@@ -71,7 +71,7 @@ if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     path = os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md")
     with open(path, "w") as out:
-        out.write(f"# ncu summary {tag}\n\nCommand profiled: `python bench.py --steps 5 --warmup 3 --no-cpu` (launch list) and `--steps 3 --warmup 3` (full capture), 4096 soft-torso envs, 1 B200.\n\n")
+        out.write(f"# ncu summary {tag}\n\nCommands (scripts/profile_round.sh): `ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 260 -c 400 python bench.py --steps 40 --warmup 10 --preroll 60 --no-cpu` (launch list) and `ncu --set full --clock-control none --import-source on -k regex:solve_kernel -s 150 -c 2` on the same command (full capture: one step launch and one reset-preparation launch), 4096 soft-torso envs, 1 B200.\n\n")
         launches(lcsv, out)
         full(rep, out, pattern)
     print(open(path).read())
