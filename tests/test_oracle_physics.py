@@ -515,3 +515,86 @@ def test_ur5e_model_has_an_inert_seventh_arm_slot(O):
     q, v, _, _ = e.get_state()
     assert q[6] == 0.0 and v[6] == 0.0
     assert np.isfinite(q).all() and np.abs(v[:6]).max() < 5.0
+
+
+def _arm_scans_numpy(link, tool, q, qd, grav, nj=7):
+    """numpy mirror of the lane-per-link formulation of csrc/arm_warp.cuh: every recursion over the chain as a scan over 8 lanes
+    (Hillis-Steele prefix product for the kinematics, prefix sums for the velocities, ONE suffix sum of link force / moment / mass /
+    first moment / inertia about the grip site), M from the broadcast spatial forces of unit joint accelerations."""
+    W = 8
+    R = [np.eye(3) for _ in range(W)]
+    t = [np.zeros(3) for _ in range(W)]
+    for j in range(nj):
+        c, s_ = np.cos(q[j]), np.sin(q[j])
+        R[j] = link[j, 3:12].reshape(3, 3) @ np.array([[c, -s_, 0], [s_, c, 0], [0, 0, 1.0]])
+        t[j] = link[j, 0:3].copy()
+    R[nj], t[nj] = tool[3:12].reshape(3, 3).copy(), tool[0:3].copy()  # lane NJ: tool transform -> grip-site pose
+    d = 1
+    while d < W:  # inclusive prefix product of (R, t): (Ra, ta) o (Rb, tb) = (Ra Rb, ta + Ra tb)
+        Rn, tn = [x.copy() for x in R], [x.copy() for x in t]
+        for j in range(d, W):
+            Rn[j], tn[j] = R[j - d] @ R[j], t[j - d] + R[j - d] @ t[j]
+        R, t, d = Rn, tn, 2 * d
+    p = np.array(t[:nj]); z = np.array([R[j][:, 2] for j in range(nj)]); site, Rs = t[nj], R[nj]
+    shift = lambda a: np.vstack([np.zeros((1, 3)), a[:-1]])
+    zq = qd[:nj, None] * z
+    w = np.cumsum(zq, 0); wp = shift(w)
+    al = np.cumsum(np.cross(wp, zq), 0); alp = shift(al)
+    r = p - shift(p)
+    ac = np.cumsum(np.cross(alp, r) + np.cross(wp, np.cross(wp, r)), 0) - grav
+    m = link[:nj, 15]
+    cl = np.array([R[j] @ link[j, 12:15] for j in range(nj)])
+    Iw = []
+    for j in range(nj):
+        I6 = link[j, 16:22]
+        I = np.array([[I6[0], I6[3], I6[4]], [I6[3], I6[1], I6[5]], [I6[4], I6[5], I6[2]]])
+        Iw.append(R[j] @ I @ R[j].T)
+    Iw = np.array(Iw)
+    acom = ac + np.cross(al, cl) + np.cross(w, np.cross(w, cl))
+    f = m[:, None] * acom
+    nn = np.einsum("jab,jb->ja", Iw, al) + np.cross(w, np.einsum("jab,jb->ja", Iw, w))
+    dd = p + cl - site
+    n0 = nn + np.cross(dd, f)
+    Icomp = Iw + m[:, None, None] * (np.einsum("ja,ja->j", dd, dd)[:, None, None] * np.eye(3) - np.einsum("ja,jb->jab", dd, dd))
+    suf = lambda a: np.cumsum(a[::-1], 0)[::-1]
+    Fs, Ns, cm, hs, Ic = suf(f), suf(n0), suf(m), suf(m[:, None] * dd), suf(Icomp)
+    a = p - site
+    bias = np.einsum("ja,ja->j", z, Ns - np.cross(a, Fs))
+    fj = np.cross(z, hs - cm[:, None] * a)
+    njv = np.einsum("jab,jb->ja", Ic, z) - np.cross(hs, np.cross(z, a))
+    M = np.eye(7)
+    for c in range(nj):
+        for i in range(c + 1):
+            M[i, c] = M[c, i] = z[i] @ (njv[c] - np.cross(a[i], fj[c]))
+    J = np.zeros((6, 7))
+    J[:3, :nj] = np.cross(z, site - p).T
+    J[3:, :nj] = z.T
+    return M, bias, J, site, Rs
+
+
+@pytest.mark.parametrize("robot", ["panda", "ur5e"])
+def test_lane_per_link_formulation_matches_the_generic_tree(O, robot):
+    """CPU pin of the arm kernel's algebra: the scan formulation of csrc/arm_warp.cuh (numpy mirror above, on the SAME link / tool
+    tables the kernel reads) against the oracle's generic-tree quantities -- joint-space inertia, bias at non-zero velocity
+    (Coriolis / centrifugal + gravity), grip-site Jacobian and pose -- for the Panda and the 6-joint UR5e."""
+    from rui_b200.env import packed_model
+    from rui_b200.model import ur5e_params
+    pk = packed_model(False, ur5e_params()) if robot == "ur5e" else packed_model(False)
+    m = pk.model
+    nj = len(m.params.link_pos)
+    e = O.OracleEnv(pk, _cfg(CC_FIXED), 0)
+    e.reset()
+    q_full, v_full = e.get_state()[0].copy(), e.get_state()[1].copy()
+    rng = np.random.default_rng(3)
+    for trial in range(5):
+        q = np.zeros(7); qd = np.zeros(7)
+        q[:nj] = np.array(m.params.init_qpos)[:nj] + rng.uniform(-0.4, 0.4, nj)
+        qd[:nj] = rng.uniform(-1.0, 1.0, nj)
+        q_full[:7], v_full[:7] = q, qd
+        e.set_state(qpos=q_full, qvel=v_full)
+        e.forward()
+        M, bias, J, site, Rs = _arm_scans_numpy(np.asarray(m.arm_link).reshape(7, 22), np.asarray(m.arm_tool), q, qd, np.array([0, 0, -9.81]), nj)
+        Jo, pos, mat = e.eef()
+        assert np.abs(M[:nj, :nj] - e.M[:nj, :nj]).max() < 1e-10
+        assert np.abs(bias[:nj] - e.bias[:nj]).max() < 1e-9
+        assert np.abs(J - Jo).max() < 1e-12 and np.abs(site - pos).max() < 1e-12 and np.abs(Rs - mat).max() < 1e-12
